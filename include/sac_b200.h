@@ -1,0 +1,130 @@
+/* sac_b200.h -- C ABI of libsac_b200.so, the B200-native encode path of the Sac lossless audio codec.
+ *
+ * The reference (slmdev/sac v0.7.25, one CPU binary) has no plugin interface; this ABI sits behind the two seams of
+ * its frame coder and is what a cgo/ctypes/C++ host binds:
+ *
+ *   population seam   Opt::eval_points_mt(func, points)          /root/reference src/opt/opt.h:25, src/opt/opt.cpp:11-43
+ *                     with func = FrameCoder::Optimize's cost lambda  src/libsac/libsac.cpp:389-397
+ *                     -> sac_eval_population / sac_eval_jobs
+ *   search            Opt::run(func, xstart) for OptDDS          src/opt/opt.h:20, src/opt/dds.cpp:33-119
+ *                     -> sac_dds_run (host; any evaluator through a callback)
+ *   frame seam        FrameCoder::{SetNumSamples,Predict,Encode,WriteEncoded}  src/libsac/libsac.h:45-56
+ *                     as driven by Codec::EncodeFile             src/libsac/libsac.cpp:822-829
+ *                     -> sac_frames_encode ; inverse (ReadEncoded,Decode,Unpredict) -> sac_frame_decode
+ *   file              Codec::EncodeFile / DecodeFile             src/libsac/libsac.cpp:782-883
+ *                     -> sac_encode_file / sac_decode_file
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, integer status (0 = ok, <0 = error, see
+ * sac_last_error()), no exceptions cross the boundary. All sample planes are planar int32 HOST memory unless a
+ * function says otherwise. Every compute entry point needs a CUDA device (sm_100a); without one sac_engine_create
+ * fails with SAC_E_NODEVICE -- there is no CPU fallback.
+ */
+#ifndef SAC_B200_H
+#define SAC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAC_PROFILE_SIZE 58   /* src/libsac/profile.cpp:10 */
+#define SAC_SEARCH_DIMS 56    /* all but coefficients 56,57 (src/libsac/libsac.cpp:469-475) */
+
+enum { SAC_OK = 0, SAC_E_NODEVICE = -1, SAC_E_CUDA = -2, SAC_E_ARG = -3, SAC_E_IO = -4, SAC_E_FORMAT = -5, SAC_E_UNSUPPORTED = -6 };
+/* FrameCoder::SearchCost (src/libsac/libsac.h:14) */
+enum { SAC_COST_L1 = 0, SAC_COST_RMS = 1, SAC_COST_ENTROPY = 2, SAC_COST_GOLOMB = 3, SAC_COST_BITPLANE = 4 };
+
+typedef struct sac_engine sac_engine; /* one per GPU: stream, HBM pools, model tables */
+typedef struct sac_window sac_window; /* samples of one (sub)frame resident in HBM + its stats */
+
+const char *sac_version(void);
+const char *sac_last_error(void);
+int sac_device_count(void);
+
+/* ---- engine ---------------------------------------------------------------------------------------------------- */
+sac_engine *sac_engine_create(int device);
+void sac_engine_destroy(sac_engine *);
+/* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
+long long sac_engine_launches(const sac_engine *);
+/* device time (ms, CUDA events on the engine's stream) and launches of the last call, by kernel class:
+ * [0] predictor [1] bitplane [2] entropy/other; out_ms[3], out_launches[3] */
+void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_launches);
+
+/* ---- profile (SacProfile::LoadBaseProfile, src/libsac/profile.cpp:3-89) ------------------------------------------ */
+int sac_base_profile(float *vmin, float *vmax, float *vdef); /* 58 each; returns 58 */
+
+/* ---- windows ---------------------------------------------------------------------------------------------------- */
+/* planes[ch][numsamples] must already be mean-free (FrameCoder::Predict, libsac.cpp:452-458);
+ * minmax = {min0,max0[,min1,max1]} after mean removal. Copies to HBM. */
+sac_window *sac_window_create(sac_engine *, int nch, const int32_t *const *planes, int numsamples, const int32_t *minmax);
+void sac_window_destroy(sac_window *);
+
+/* ---- FrameCoder::PredictFrame (libsac.cpp:94-142) for P profiles at once ------------------------------------------
+ * profiles[P][58]; window [from, from+n); k = OLS solve interval; resid[P][nch][n] (host) receives the residuals
+ * in channel-index order. flags[P] (may be null): 1 if a prediction became non-finite. */
+int sac_predict(sac_engine *, const sac_window *, const float *profiles, int P, int from, int n, int k, int32_t *resid,
+                int *flags);
+
+/* ---- CostFunction::Calc (src/libsac/cost.h) on host residual arrays: bufs[count][n] -> cost[count] ---------------- */
+int sac_cost(sac_engine *, int cost_kind, const int32_t *bufs, int count, int n, double *cost);
+
+/* ---- population evaluation -------------------------------------------------------------------------------------
+ * cost[p] = sum over channels of Cost(PredictFrame(profile with dims[i] <- (float)X[p][i], window, k=optk)).
+ * Non-finite predictor state gives cost = +INF. One call in flight per engine. */
+int sac_eval_population(sac_engine *, const sac_window *, int from, int n, const float *base_profile, const int *dims,
+                        int D, const double *X, int P, int cost_kind, int optk, double *cost);
+/* the same over several windows in one batch: job j evaluates X[j] on wins[j] with bases[j] (58 floats each) */
+int sac_eval_jobs(sac_engine *, int njobs, const sac_window *const *wins, const int *from, const int *n,
+                  const float *bases, const int *dims, int D, const double *X, int cost_kind, int optk, double *cost);
+
+/* ---- DDS (OptDDS, src/opt/dds.cpp) ------------------------------------------------------------------------------
+ * eval(X[P][D], P, cost[P], user) fills costs; returns non-zero to abort. num_threads<=0: run_single (SSC0);
+ * >0: run_mt with generations of num_threads (SSC1). mt19937 seed 0 as src/opt/opt.cpp:5. Returns best cost. */
+typedef int (*sac_eval_fn)(const double *X, int P, int D, double *cost, void *user);
+double sac_dds_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
+                   double sigma_init, sac_eval_fn eval, void *user, double *xbest);
+
+/* ---- frame coding ------------------------------------------------------------------------------------------------ */
+typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac/libsac.h:19-44) */
+  int optimize;                 /* 0 = --normal */
+  double fraction;              /* window fraction of max_framesize */
+  int maxnfunc;                 /* DDS evaluations per frame */
+  int num_threads;              /* DDS generation size (0 = sequential run_single) */
+  double sigma;                 /* initial DDS radius */
+  int optk;                     /* OLS solve interval during search (4) */
+  int cost_kind;                /* SAC_COST_* */
+  int reset;                    /* --opt-reset: every frame starts from the base profile */
+  int zero_mean;                /* 1 */
+  int sparse_pcm;               /* accepted for CLI compatibility; sparse mapping is not implemented (never smaller below ratio 1.05) */
+  int max_framelen;             /* seconds (20) */
+  int adapt_block;              /* accepted; adaptive splitting is not implemented (one sub-frame per read) */
+  int frame_parallel;           /* B200 extension: search all frames of a call concurrently (implies reset semantics) */
+  int verbose;
+} sac_cfg;
+void sac_cfg_default(sac_cfg *);
+/* presets of src/cmdline.cpp:127-156: "normal","high","veryhigh","extrahigh","best","insane" */
+int sac_cfg_preset(sac_cfg *, const char *name);
+
+/* Predict()+Encode()+WriteEncoded() for nframes frames of one stream. planes[f*nch+ch] -> raw samples of frame f
+ * (numsamples[f] each). profile_io[58]: in = start profile of the first frame, out = profile after the last.
+ * Frame records are appended to out (cap bytes); *out_len receives the total. */
+int sac_frames_encode(sac_engine *, const sac_cfg *, int nch, int max_framesize, int nframes,
+                      const int32_t *const *planes, const int *numsamples, float *profile_io, uint8_t *out, long long cap,
+                      long long *out_len);
+/* one frame record -> samples (mean restored). Returns bytes consumed (>0) or <0. planes_out[ch][cap_samples]. */
+long long sac_frame_decode(sac_engine *, int nch, const uint8_t *in, long long len, int32_t *const *planes_out,
+                           int cap_samples, int *numsamples);
+
+/* ---- files (Codec::EncodeFile / DecodeFile, WAV and .sac containers of src/file/) ------------------------------- */
+typedef struct sac_file_stats { long long in_bytes, out_bytes; int numsamples, nch, samplerate, bits, nframes; double seconds; uint8_t md5[16]; int md5_ok; } sac_file_stats;
+int sac_encode_file(sac_engine *, const sac_cfg *, const char *wav_path, const char *sac_path, sac_file_stats *);
+int sac_decode_file(sac_engine *, const char *sac_path, const char *wav_path, sac_file_stats *);
+/* in-memory variants (host buffers) used by bench.py's e2e leg */
+int sac_encode_memory(sac_engine *, const sac_cfg *, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap,
+                      long long *out_len, sac_file_stats *);
+int sac_decode_memory(sac_engine *, const uint8_t *sac, long long sac_len, uint8_t *out, long long cap, long long *out_len,
+                      sac_file_stats *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -152,34 +152,31 @@ struct Ols {
     for (int i = 0; i < n; i++) z[i] = y[i] * invD[i];
     for (int i = n - 1; i >= 0; i--) { double s = z[i]; for (int k = i + 1; k < n; k++) s -= L[k][i] * w[k]; w[i] = s; }
   }
-  // B200 order: right-looking. Same pivots and column scaling; the rank-1 trailing update uses the unscaled
-  // column (W[c][j] = L[c][j]*D[j] up to rounding) and one fma per element, columns applied in ascending j --
-  // the same subtraction sequence per element as the left-looking loop.
+  // B200 order: right-looking LDL^T on the matrix augmented with b as row n (so the forward substitution and the
+  // D^-1 scaling fall out of the factorisation: row n of L is z = D^-1 L^-1 b). Same pivots and column scaling as
+  // the reference; the rank-1 trailing update uses the unscaled column W[c][j] (= L[c][j]*D[j] up to rounding) and
+  // one fma per element, columns applied in ascending j. Back substitution column-oriented, k descending.
   std::vector<vec> W;
-  bool FactorB200()
+  vec lcol;
+  bool FactorSolveB200()
   {
-    if (W.empty()) W.assign(n, vec(n));
+    if (W.empty()) { W.assign(n + 1, vec(n + 1)); lcol.assign(n + 1, 0.0); }
     for (int i = 0; i < n; i++) { for (int c = 0; c <= i; c++) W[i][c] = mcov[i][c]; W[i][i] = W[i][i] + nu; }
+    for (int c = 0; c < n; c++) W[n][c] = b[c];
     for (int j = 0; j < n; j++) {
       const double dj = W[j][j];
       if (dj < 1e-12) return false;
       const double inv = 1.0 / dj;
-      D[j] = dj; invD[j] = inv;
-      for (int i = j + 1; i < n; i++) L[i][j] = W[i][j] * inv;
-      for (int i = j + 1; i < n; i++)
-        for (int c = j + 1; c <= i; c++) W[i][c] = std::fma(-L[i][j], W[c][j], W[i][c]);
+      for (int i = j + 1; i <= n; i++) lcol[i] = W[i][j] * inv;
+      for (int i = j + 1; i <= n; i++)
+        for (int c = j + 1; c <= i && c < n; c++) W[i][c] = std::fma(-lcol[i], W[c][j], W[i][c]);
+      for (int i = j + 1; i <= n; i++) W[i][j] = lcol[i];
     }
-    return true;
-  }
-  // column-oriented substitutions, one fma per element: forward k ascending, backward k descending
-  void SolveB200()
-  {
-    for (int i = 0; i < n; i++) y[i] = b[i];
-    for (int k = 0; k < n; k++)
-      for (int i = k + 1; i < n; i++) y[i] = std::fma(-L[i][k], y[k], y[i]);
-    for (int i = 0; i < n; i++) w[i] = y[i] * invD[i];
+    for (int i = 0; i < n; i++) y[i] = W[n][i];
     for (int k = n - 1; k >= 0; k--)
-      for (int i = 0; i < k; i++) w[i] = std::fma(-L[k][i], w[k], w[i]);
+      for (int i = 0; i < k; i++) y[i] = std::fma(-W[k][i], y[k], y[i]);
+    for (int i = 0; i < n; i++) w[i] = y[i];
+    return true;
   }
   // ref ols.cpp:27-57
   void Update(double val)
@@ -195,7 +192,7 @@ struct Ols {
     }
     km++;
     if (km >= kmax) {
-      if (b200()) { if (FactorB200()) SolveB200(); }
+      if (b200()) FactorSolveB200();
       else { if (FactorRef()) SolveRef(); }
       km = 0;
     }

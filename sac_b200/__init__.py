@@ -1,0 +1,263 @@
+"""sac_b200 -- Python binding (ctypes) of libsac_b200.so, the B200-native encode path of the Sac lossless audio codec.
+
+The product is the C ABI in include/sac_b200.h (CUDA kernels for sm_100a behind plain pointers and sizes); this
+module only loads it and mirrors the reference's frame-coder surface (/root/reference src/libsac/libsac.h:45-56,
+src/opt/opt.h:17-25) for tests and bench.py. There is no CPU fallback: without the built library or without a GPU
+every compute call raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsac_b200.so")
+CLI_PATH = os.path.join(_HERE, "sac")
+
+PROFILE_SIZE = 58
+SEARCH_DIMS = [i for i in range(58) if i not in (56, 57)]
+COST_L1, COST_RMS, COST_ENTROPY, COST_GOLOMB, COST_BITPLANE = range(5)
+
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_intp = C.POINTER(C.c_int)
+EVAL_FN = C.CFUNCTYPE(C.c_int, _f64p, C.c_int, C.c_int, _f64p, C.c_void_p)
+
+
+class SacError(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    """sac_cfg (FrameCoder::tsac_cfg / toptim_cfg, libsac.h:19-44)"""
+    _fields_ = [("optimize", C.c_int), ("fraction", C.c_double), ("maxnfunc", C.c_int), ("num_threads", C.c_int),
+                ("sigma", C.c_double), ("optk", C.c_int), ("cost_kind", C.c_int), ("reset", C.c_int), ("zero_mean", C.c_int),
+                ("sparse_pcm", C.c_int), ("max_framelen", C.c_int), ("adapt_block", C.c_int), ("frame_parallel", C.c_int),
+                ("verbose", C.c_int)]
+
+
+class FileStats(C.Structure):
+    _fields_ = [("in_bytes", C.c_longlong), ("out_bytes", C.c_longlong), ("numsamples", C.c_int), ("nch", C.c_int),
+                ("samplerate", C.c_int), ("bits", C.c_int), ("nframes", C.c_int), ("seconds", C.c_double),
+                ("md5", C.c_uint8 * 16), ("md5_ok", C.c_int)]
+
+
+def build(verbose=False):
+    """compile libsac_b200.so and the sac CLI in-tree for sm_100a (nvcc cross-compiles without a GPU)"""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"] + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SacError("libsac_b200.so is not built (run sac_b200.build() / make -C sac_b200/csrc); there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        L.sac_version.restype = C.c_char_p
+        L.sac_last_error.restype = C.c_char_p
+        L.sac_engine_create.restype = C.c_void_p
+        L.sac_engine_create.argtypes = [C.c_int]
+        L.sac_engine_destroy.argtypes = [C.c_void_p]
+        L.sac_engine_launches.restype = C.c_longlong
+        L.sac_engine_launches.argtypes = [C.c_void_p]
+        L.sac_engine_last_timing.argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_longlong)]
+        L.sac_window_create.restype = C.c_void_p
+        L.sac_window_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(_i32p), C.c_int, _i32p]
+        L.sac_window_destroy.argtypes = [C.c_void_p]
+        L.sac_predict.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _intp]
+        L.sac_cost.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int, C.c_int, _f64p]
+        L.sac_eval_population.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _f32p, _intp, C.c_int, _f64p, C.c_int,
+                                          C.c_int, C.c_int, _f64p]
+        L.sac_eval_jobs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _intp, _intp, _f32p, _intp, C.c_int, _f64p,
+                                    C.c_int, C.c_int, _f64p]
+        L.sac_dds_run.restype = C.c_double
+        L.sac_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
+        L.sac_cfg_default.argtypes = [C.POINTER(Cfg)]
+        L.sac_cfg_preset.argtypes = [C.POINTER(Cfg), C.c_char_p]
+        L.sac_frames_encode.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_int, C.c_int, C.c_int, C.POINTER(_i32p), _intp, _f32p,
+                                        _u8p, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sac_frame_decode.restype = C.c_longlong
+        L.sac_frame_decode.argtypes = [C.c_void_p, C.c_int, _u8p, C.c_longlong, C.POINTER(_i32p), C.c_int, _intp]
+        L.sac_encode_file.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
+        L.sac_decode_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
+        L.sac_encode_memory.argtypes = [C.c_void_p, C.POINTER(Cfg), _u8p, C.c_longlong, _u8p, C.c_longlong,
+                                        C.POINTER(C.c_longlong), C.POINTER(FileStats)]
+        L.sac_decode_memory.argtypes = [C.c_void_p, _u8p, C.c_longlong, _u8p, C.c_longlong, C.POINTER(C.c_longlong),
+                                        C.POINTER(FileStats)]
+        _lib = L
+    return _lib
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise SacError("%s failed (%d): %s" % (what, rc, lib().sac_last_error().decode()))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def base_profile():
+    vmin = np.zeros(58, np.float32); vmax = np.zeros(58, np.float32); vdef = np.zeros(58, np.float32)
+    lib().sac_base_profile(_p(vmin, _f32p), _p(vmax, _f32p), _p(vdef, _f32p))
+    return vmin, vmax, vdef
+
+
+def make_cfg(preset=None, **kw):
+    c = Cfg()
+    lib().sac_cfg_default(C.byref(c))
+    if preset:
+        _chk(lib().sac_cfg_preset(C.byref(c), preset.encode()), "sac_cfg_preset")
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def dds_run(func, xmin, xmax, xstart, nfunc_max, num_threads=0, sigma_init=0.2):
+    """OptDDS::run with a Python population evaluator func(X[P,D]) -> costs[P] (host only, no GPU needed)"""
+    xmin = np.ascontiguousarray(xmin, np.float64); xmax = np.ascontiguousarray(xmax, np.float64)
+    xstart = np.ascontiguousarray(xstart, np.float64)
+    D = len(xstart)
+    xbest = np.zeros(D)
+
+    def cb(Xp, P, Dd, costp, _user):
+        X = np.ctypeslib.as_array(Xp, shape=(P, Dd))
+        out = np.ctypeslib.as_array(costp, shape=(P,))
+        out[:] = np.asarray(func(X.copy()), np.float64)
+        return 0
+
+    fn = EVAL_FN(cb)
+    best = lib().sac_dds_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, num_threads, sigma_init, fn, None,
+                             _p(xbest, _f64p))
+    return best, xbest
+
+
+class Window:
+    """a (sub)frame resident in HBM: mean-free planes + stats (what FrameCoder::Optimize's cost lambda captures)"""
+
+    def __init__(self, engine, planes, minmax):
+        self.engine = engine
+        self.nch = len(planes)
+        self.n = len(planes[0])
+        self._planes = [np.ascontiguousarray(p, np.int32) for p in planes]
+        arr = (_i32p * self.nch)(*[_p(p, _i32p) for p in self._planes])
+        mm = np.ascontiguousarray(minmax, np.int32)
+        self.h = lib().sac_window_create(engine.h, self.nch, arr, self.n, _p(mm, _i32p))
+        if not self.h:
+            raise SacError("sac_window_create: " + lib().sac_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().sac_window_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.h = lib().sac_engine_create(device)
+        if not self.h:
+            raise SacError("sac_engine_create: " + lib().sac_last_error().decode())
+
+    def close(self):
+        if self.h:
+            lib().sac_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib().sac_engine_launches(self.h))
+
+    def last_timing(self):
+        ms = (C.c_double * 3)(); ln = (C.c_longlong * 3)()
+        lib().sac_engine_last_timing(self.h, ms, ln)
+        return list(ms), list(ln)
+
+    def window(self, planes, minmax):
+        return Window(self, planes, minmax)
+
+    def predict(self, win, profiles, frm, n, k):
+        """FrameCoder::PredictFrame for P profiles: returns residuals [P, nch, n] and flags [P]"""
+        profiles = np.ascontiguousarray(np.atleast_2d(profiles), np.float32)
+        P = profiles.shape[0]
+        out = np.zeros((P, win.nch, n), np.int32)
+        flags = np.zeros(P, np.int32)
+        _chk(lib().sac_predict(self.h, win.h, _p(profiles, _f32p), P, frm, n, k, _p(out, _i32p), _p(flags, _intp)), "sac_predict")
+        return out, flags
+
+    def cost(self, kind, bufs):
+        bufs = np.ascontiguousarray(np.atleast_2d(bufs), np.int32)
+        out = np.zeros(bufs.shape[0])
+        _chk(lib().sac_cost(self.h, kind, _p(bufs, _i32p), bufs.shape[0], bufs.shape[1], _p(out, _f64p)), "sac_cost")
+        return out
+
+    def eval_population(self, win, frm, n, base, X, cost_kind, optk=4, dims=None):
+        """Opt::eval_points_mt over the cost lambda of FrameCoder::Optimize: X[P,D] -> cost[P]"""
+        X = np.ascontiguousarray(np.atleast_2d(X), np.float64)
+        dims = np.ascontiguousarray(SEARCH_DIMS if dims is None else dims, np.int32)
+        base = np.ascontiguousarray(base, np.float32)
+        out = np.zeros(X.shape[0])
+        _chk(lib().sac_eval_population(self.h, win.h, frm, n, _p(base, _f32p), _p(dims, _intp), X.shape[1], _p(X, _f64p), X.shape[0],
+                                       cost_kind, optk, _p(out, _f64p)), "sac_eval_population")
+        return out
+
+    def frames_encode(self, cfg, frames, max_framesize, profile=None):
+        """frames: list of lists of int32 planes (raw samples). Returns (bytes, profile_out)."""
+        nch = len(frames[0])
+        keep = [[np.ascontiguousarray(p, np.int32) for p in fr] for fr in frames]
+        flat = [p for fr in keep for p in fr]
+        arr = (_i32p * len(flat))(*[_p(p, _i32p) for p in flat])
+        ns = np.array([len(fr[0]) for fr in keep], np.int32)
+        prof = np.ascontiguousarray(base_profile()[2] if profile is None else profile, np.float32).copy()
+        cap = int(sum(int(x) for x in ns) * nch * 5 + 4096 * len(keep))
+        out = np.zeros(cap, np.uint8)
+        olen = C.c_longlong(0)
+        _chk(lib().sac_frames_encode(self.h, C.byref(cfg), nch, max_framesize, len(keep), arr, _p(ns, _intp), _p(prof, _f32p),
+                                     _p(out, _u8p), cap, C.byref(olen)), "sac_frames_encode")
+        return out[:olen.value].copy(), prof
+
+    def frame_decode(self, nch, data, cap_samples):
+        data = np.ascontiguousarray(data, np.uint8)
+        planes = [np.zeros(cap_samples, np.int32) for _ in range(nch)]
+        arr = (_i32p * nch)(*[_p(p, _i32p) for p in planes])
+        n = C.c_int(0)
+        used = lib().sac_frame_decode(self.h, nch, _p(data, _u8p), len(data), arr, cap_samples, C.byref(n))
+        if used < 0:
+            raise SacError("sac_frame_decode failed (%d): %s" % (used, lib().sac_last_error().decode()))
+        return [p[:n.value] for p in planes], int(used)
+
+    def encode_memory(self, cfg, wav_bytes):
+        wav = np.frombuffer(wav_bytes, np.uint8)
+        cap = len(wav) * 2 + 65536
+        out = np.zeros(cap, np.uint8)
+        olen = C.c_longlong(0)
+        st = FileStats()
+        _chk(lib().sac_encode_memory(self.h, C.byref(cfg), _p(wav, _u8p), len(wav), _p(out, _u8p), cap, C.byref(olen), C.byref(st)),
+             "sac_encode_memory")
+        return out[:olen.value].tobytes(), st
+
+    def decode_memory(self, sac_bytes, cap):
+        sac = np.frombuffer(sac_bytes, np.uint8)
+        out = np.zeros(cap, np.uint8)
+        olen = C.c_longlong(0)
+        st = FileStats()
+        _chk(lib().sac_decode_memory(self.h, _p(sac, _u8p), len(sac), _p(out, _u8p), cap, C.byref(olen), C.byref(st)), "sac_decode_memory")
+        return out[:olen.value].tobytes(), st

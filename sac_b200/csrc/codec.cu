@@ -1,0 +1,785 @@
+// codec.cu -- frame and file level of the codec on top of the engine:
+//   FrameCoder::Predict / Optimize / Encode / WriteEncoded   (/root/reference src/libsac/libsac.cpp:365-578)
+//   FrameCoder::ReadEncoded / Decode / Unpredict             (src/libsac/libsac.cpp:144-199,280-298,580-593)
+//   Codec::EncodeFile / DecodeFile                            (src/libsac/libsac.cpp:782-883)
+//   OptDDS, SSC0/SSC1                                         (src/opt/dds.cpp, src/opt/ssc.h, src/opt/opt.cpp:111-166)
+//   Wav / Chunks / Sac containers, MD5                        (src/file/wav.cpp, src/file/sac.cpp, src/common/md5.cpp)
+// The search loop and the containers are host code; every sample-touching step runs in the kernels.
+#include "codec.h"
+#include "engine.h"
+#include <algorithm>
+#include <cctype>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+
+namespace sacb {
+
+// =====================================================================================================================
+// DDS
+// =====================================================================================================================
+DdsSearch::DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
+                     double sigma_init)
+    : D_(D), nfunc_max_(nfunc_max), num_threads_(num_threads), xmin_(xmin, xmin + D), xmax_(xmax, xmax + D), xb_(xstart, xstart + D),
+      sigma_(sigma_init)
+{
+}
+double DdsSearch::reflect(double xnew, double lo, double hi) const      // opt.cpp:156-166
+{
+  if (xnew < lo) { xnew = lo + (lo - xnew); if (xnew > hi) xnew = lo; }
+  if (xnew > hi) { xnew = hi - (xnew - hi); if (xnew < lo) xnew = hi; }
+  return xnew;
+}
+std::vector<double> DdsSearch::candidate(int nfunc)                     // dds.cpp:12-31
+{
+  std::vector<int> J;
+  const double p = 1.0 - std::log(nfunc) / std::log(nfunc_max_);
+  for (int i = 0; i < D_; i++)
+    if (std::uniform_real_distribution<double>{0, 1}(eng_) < p) J.push_back(i);
+  if (J.empty()) J.push_back((int)std::uniform_int_distribution<uint32_t>{0u, (uint32_t)(D_ - 1)}(eng_));
+  std::vector<double> xt = xb_;
+  for (int k : J) {
+    const double s = sigma_ * (xmax_[k] - xmin_[k]);                    // opt.cpp:111-116
+    xt[k] = reflect(xb_[k] + s * std::normal_distribution<double>{0.0, 1.0}(eng_), xmin_[k], xmax_[k]);
+  }
+  return xt;
+}
+void DdsSearch::propose(std::vector<std::vector<double>> &cands)
+{
+  cands.clear();
+  if (!started_) { cands.push_back(xb_); pending_ = cands; return; }
+  const int nt = num_threads_ <= 0 ? 1 : std::min(nfunc_max_ - nfunc_, num_threads_);
+  for (int i = 0; i < nt; i++) { cands.push_back(candidate(nfunc_)); nfunc_++; }
+  pending_ = cands;
+}
+void DdsSearch::consume(const double *costs)
+{
+  if (!started_) { fb_ = costs[0]; nfunc_ = 1; started_ = true; return; }
+  const int nt = (int)pending_.size();
+  if (num_threads_ <= 0) {                                              // run_single + SSC0 (ssc.h:6-37)
+    const bool ok = costs[0] < fb_;
+    if (ok) { xb_ = pending_[0]; fb_ = costs[0]; nsucc_ += 1; nfail_ = 0; } else { nsucc_ = 0; nfail_ += 1; }
+    if (nsucc_ >= 3) { sigma_ = sigma_ * 2.0; nsucc_ = 0; } else if (nfail_ >= 50) { sigma_ = sigma_ / 2.0; nfail_ = 0; }
+    sigma_ = std::clamp(sigma_, 0.05, 0.5);
+  } else {                                                              // run_mt + SSC1 (dds.cpp:88-98, ssc.h:40-60)
+    const double fb_old = fb_;
+    int nsucc = 0;
+    for (int i = 0; i < nt; i++)
+      if (costs[i] < fb_old) { nsucc++; if (costs[i] < fb_) { fb_ = costs[i]; xb_ = pending_[i]; } }
+    const double lambda = nsucc / static_cast<double>(nt);
+    p_succ_ = (1.0 - 0.10) * p_succ_ + 0.10 * lambda;
+    sigma_ = sigma_ * std::exp(0.05 * (p_succ_ - 0.05) / (1.0 - 0.05));
+    sigma_ = std::clamp(sigma_, 0.05, 0.25);
+  }
+}
+
+// =====================================================================================================================
+// MD5
+// =====================================================================================================================
+namespace {
+const uint32_t kMd5K[64] = {
+    0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501, 0x698098d8, 0x8b44f7af, 0xffff5bb1,
+    0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821, 0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453,
+    0xd8a1e681, 0xe7d3fbc8, 0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a, 0xfffa3942,
+    0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70, 0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05,
+    0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665, 0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d,
+    0x85845dd1, 0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+const int kMd5S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
+                       4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+inline uint32_t rol(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
+void md5_block(Md5 &m, const uint8_t *p)
+{
+  uint32_t w[16];
+  for (int i = 0; i < 16; i++) w[i] = p[4 * i] | (p[4 * i + 1] << 8) | (p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+  uint32_t a = m.a, b = m.b, c = m.c, d = m.d;
+  for (int i = 0; i < 64; i++) {
+    uint32_t f; int g;
+    if (i < 16) { f = (b & c) | (~b & d); g = i; }
+    else if (i < 32) { f = (d & b) | (~d & c); g = (5 * i + 1) & 15; }
+    else if (i < 48) { f = b ^ c ^ d; g = (3 * i + 5) & 15; }
+    else { f = c ^ (b | ~d); g = (7 * i) & 15; }
+    const uint32_t t = d; d = c; c = b;
+    b = b + rol(a + f + kMd5K[i] + w[g], kMd5S[i]);
+    a = t;
+  }
+  m.a += a; m.b += b; m.c += c; m.d += d;
+}
+} // namespace
+Md5::Md5() : a(0x67452301), b(0xefcdab89), c(0x98badcfe), d(0x10325476), len(0), fill(0) {}
+void Md5::update(const uint8_t *p, size_t n)
+{
+  len += n;
+  while (n) {
+    const size_t take = std::min(n, (size_t)(64 - fill));
+    std::memcpy(buf + fill, p, take);
+    fill += (int)take; p += take; n -= take;
+    if (fill == 64) { md5_block(*this, buf); fill = 0; }
+  }
+}
+void Md5::final(uint8_t out[16])
+{
+  const uint64_t bits = len * 8;
+  uint8_t pad[72] = {0x80};
+  const size_t padlen = (fill < 56) ? (56 - fill) : (120 - fill);
+  update(pad, padlen);
+  uint8_t lb[8];
+  for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (8 * i));
+  update(lb, 8);
+  const uint32_t v[4] = {a, b, c, d};
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(v[i] >> (8 * j));
+}
+
+// =====================================================================================================================
+// WAV / metadata
+// =====================================================================================================================
+namespace {
+inline uint32_t get32(const uint8_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24); }
+inline uint16_t get16(const uint8_t *b) { return (uint16_t)(b[0] | (b[1] << 8)); }
+inline void put32(uint8_t *b, uint32_t v) { b[0] = v & 0xff; b[1] = (v >> 8) & 0xff; b[2] = (v >> 16) & 0xff; b[3] = (v >> 24) & 0xff; }
+inline void put16(uint8_t *b, uint16_t v) { b[0] = v & 0xff; b[1] = (v >> 8) & 0xff; }
+inline void push32(std::vector<uint8_t> &o, uint32_t v) { uint8_t b[4]; put32(b, v); o.insert(o.end(), b, b + 4); }
+inline void push16(std::vector<uint8_t> &o, uint16_t v) { uint8_t b[2]; put16(b, v); o.insert(o.end(), b, b + 2); }
+inline uint32_t word_align(uint32_t n) { return (n & 1) ? n + 1 : n; }
+constexpr uint32_t kRIFF = 0x46464952, kWAVE = 0x45564157, kFMT = 0x20746d66, kDATA = 0x61746164;
+} // namespace
+
+uint32_t WavInfo::metadatasize() const
+{
+  uint32_t t = 0;
+  for (auto &c : chunks) t += 8 + (uint32_t)c.data.size();
+  return t;
+}
+
+// Wav::ReadHeader (wav.cpp:167-263)
+int wav_parse(const uint8_t *f, size_t len, WavInfo &wi)
+{
+  if (len < 12 || get32(f) != kRIFF || get32(f + 8) != kWAVE) { set_error("input is not a valid .wav file"); return SAC_E_FORMAT; }
+  wi.chunks.clear();
+  wi.chunks.push_back({kRIFF, get32(f + 4), std::vector<uint8_t>(f + 8, f + 12)});
+  size_t pos = 12;
+  bool have_fmt = false, have_data = false;
+  while (true) {
+    if (pos + 8 > len) { if (have_data) break; set_error("could not read wav chunk"); return SAC_E_FORMAT; }
+    const uint32_t id = get32(f + pos), cs = get32(f + pos + 4);
+    pos += 8;
+    if (id == kFMT) {
+      if ((cs != 16 && cs != 18 && cs != 40) || pos + cs > len) { set_error("invalid fmt-chunk size"); return SAC_E_FORMAT; }
+      const uint8_t *b = f + pos;
+      int audioformat = get16(b);
+      wi.nch = get16(b + 2); wi.samplerate = (int)get32(b + 4); wi.blockalign = get16(b + 12); wi.bits = get16(b + 14);
+      if (cs >= 18) {
+        const int cb = get16(b + 16);
+        if (cb >= 22 && cs >= 40) { wi.bits = get16(b + 18); audioformat = get16(b + 24); }
+      }
+      wi.chunks.push_back({id, cs, std::vector<uint8_t>(b, b + cs)});
+      pos += cs;
+      if (audioformat != 1) { set_error("only PCM format supported"); return SAC_E_UNSUPPORTED; }
+      have_fmt = true;
+    } else if (id == kDATA) {
+      if (!have_fmt || wi.blockalign <= 0) { set_error("data chunk before fmt chunk"); return SAC_E_FORMAT; }
+      wi.chunks.push_back({id, cs, {}});
+      wi.data_pos = pos;
+      wi.numsamples = cs / wi.blockalign;
+      const size_t endofdata = pos + word_align(cs);
+      have_data = true;
+      if (endofdata >= len) {
+        if (endofdata > len) wi.numsamples = (uint32_t)((len - pos) / wi.blockalign);   // truncated data chunk (wav.cpp:238-243)
+        break;
+      }
+      pos += cs;                                                       // (the reference seeks by chunksize, not the aligned size)
+    } else {
+      const uint32_t rs = word_align(cs);
+      if (pos + rs > len) { set_error("truncated wav chunk"); return SAC_E_FORMAT; }
+      wi.chunks.push_back({id, cs, std::vector<uint8_t>(f + pos, f + pos + rs)});
+      pos += rs;
+    }
+    if (pos == len) break;
+  }
+  if (!have_data || !have_fmt) { set_error("wav file without fmt/data chunk"); return SAC_E_FORMAT; }
+  return SAC_OK;
+}
+
+// Wav::ReadSamples (wav.cpp:77-124)
+void wav_unpack(const WavInfo &wi, const uint8_t *pcm, int first, int count, std::vector<std::vector<int32_t>> &planes)
+{
+  const int cs = wi.blockalign / wi.nch;
+  const uint8_t *p = pcm + (size_t)first * wi.blockalign;
+  for (int i = 0; i < count; i++)
+    for (int k = 0; k < wi.nch; k++) {
+      int32_t v = 0;
+      if (cs == 1) { v = (int32_t)p[0] - 128; }
+      else if (cs == 2) { v = (int16_t)((p[1] << 8) | p[0]); }
+      else if (cs == 3) { int32_t s = ((int32_t)p[2] << 24) | ((int32_t)p[1] << 16) | ((int32_t)p[0] << 8); v = s >> 8; }
+      planes[k][i] = v;
+      p += cs;
+    }
+}
+// Wav::WriteSamples (wav.cpp:126-164)
+void wav_pack(const WavInfo &wi, const std::vector<std::vector<int32_t>> &planes, int count, std::vector<uint8_t> &out)
+{
+  const int cs = wi.blockalign / wi.nch;
+  const size_t o0 = out.size();
+  out.resize(o0 + (size_t)count * wi.blockalign);
+  uint8_t *p = out.data() + o0;
+  for (int i = 0; i < count; i++)
+    for (int k = 0; k < wi.nch; k++) {
+      const int32_t s = planes[k][i];
+      if (cs == 1) p[0] = (uint8_t)((s + 128) & 0xff);
+      else if (cs == 2) { p[0] = s & 0xff; p[1] = (s >> 8) & 0xff; }
+      else if (cs == 3) { p[0] = s & 0xff; p[1] = (s >> 8) & 0xff; p[2] = (s >> 16) & 0xff; }
+      p += cs;
+    }
+}
+// Chunks::PackMetaData / UnpackMetaData (wav.cpp:24-53)
+void pack_metadata(const WavInfo &wi, std::vector<uint8_t> &out)
+{
+  for (auto &c : wi.chunks) { push32(out, c.id); push32(out, c.csize); out.insert(out.end(), c.data.begin(), c.data.end()); }
+}
+int unpack_metadata(const uint8_t *p, size_t n, WavInfo &wi)
+{
+  size_t ofs = 0;
+  wi.chunks.clear();
+  while (ofs + 8 <= n) {
+    const uint32_t id = get32(p + ofs), cs = get32(p + ofs + 4);
+    ofs += 8;
+    if (id == kRIFF) { if (ofs + 4 > n) return SAC_E_FORMAT; wi.chunks.push_back({id, cs, std::vector<uint8_t>(p + ofs, p + ofs + 4)}); ofs += 4; }
+    else if (id == kDATA) wi.chunks.push_back({id, cs, {}});
+    else {
+      const uint32_t ws = word_align(cs);
+      if (ofs + ws > n) return SAC_E_FORMAT;
+      wi.chunks.push_back({id, cs, std::vector<uint8_t>(p + ofs, p + ofs + ws)});
+      ofs += ws;
+    }
+  }
+  return ofs == n ? SAC_OK : SAC_E_FORMAT;
+}
+
+// =====================================================================================================================
+// frames
+// =====================================================================================================================
+namespace {
+
+struct FrameWork {
+  int n = 0;
+  int32_t mean[2] = {0, 0}, mm[4] = {0, 0, 0, 0};
+  Window *win = nullptr;
+  float profile[kProfileSize];
+};
+
+// AnalyseMonoChannel + zero-mean (libsac.cpp:626-651, 452-458)
+void analyse_channel(std::vector<int32_t> &s, int zero_mean, int32_t &mean, int32_t &mn, int32_t &mx)
+{
+  int64_t sum = 0;
+  mn = std::numeric_limits<int32_t>::max(); mx = std::numeric_limits<int32_t>::min();
+  for (int32_t v : s) { sum += v; mx = std::max(mx, v); mn = std::min(mn, v); }
+  mean = s.empty() ? 0 : (int)std::floor(sum / (double)s.size());
+  if (!zero_mean) mean = 0;
+  else if (mean != 0) { for (auto &v : s) v -= mean; mn -= mean; mx -= mean; }
+}
+
+} // namespace
+
+static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
+                         const int *numsamples, float *profile_io, std::vector<uint8_t> &out)
+{
+  std::vector<FrameWork> fw(nframes);
+  struct Cleanup { std::vector<FrameWork> &f; ~Cleanup() { for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw};
+  // ---- analysis + upload ----
+  for (int f = 0; f < nframes; f++) {
+    FrameWork &w = fw[f];
+    w.n = numsamples[f];
+    if (w.n <= 0 || w.n > max_framesize) { set_error("frame length out of range"); return SAC_E_ARG; }
+    std::vector<std::vector<int32_t>> s(nch);
+    const int32_t *pp[2] = {nullptr, nullptr};
+    for (int ch = 0; ch < nch; ch++) {
+      s[ch].assign(planes[f * nch + ch], planes[f * nch + ch] + w.n);
+      analyse_channel(s[ch], cfg.zero_mean, w.mean[ch], w.mm[2 * ch], w.mm[2 * ch + 1]);
+      pp[ch] = s[ch].data();
+    }
+    w.win = reinterpret_cast<Window *>(sac_window_create(reinterpret_cast<sac_engine *>(e), nch, pp, w.n, w.mm));
+    if (!w.win) return SAC_E_CUDA;
+  }
+  // ---- search (FrameCoder::Optimize, libsac.cpp:365-427; Predict :461-476) ----
+  std::vector<int> dims;
+  for (int i = 0; i < kProfileSize; i++) if (i != 56 && i != 57) dims.push_back(i);
+  const int D = (int)dims.size();
+  std::vector<double> xmin(D), xmax(D);
+  for (int i = 0; i < D; i++) { xmin[i] = kBaseProfile[dims[i]][0]; xmax[i] = kBaseProfile[dims[i]][1]; }
+  float cur[kProfileSize];
+  std::memcpy(cur, profile_io, sizeof(cur));
+  auto base_reset = [&](float *p) { for (int i = 0; i < kProfileSize; i++) p[i] = kBaseProfile[i][2]; };
+
+  if (cfg.optimize && cfg.maxnfunc > 0 && cfg.fraction > 0.0) {
+    const int groups = cfg.frame_parallel ? 1 : nframes;          // frames searched together per group
+    for (int g = 0; g < groups; g++) {
+      const int f0 = cfg.frame_parallel ? 0 : g, f1 = cfg.frame_parallel ? nframes : g + 1;
+      std::vector<std::unique_ptr<DdsSearch>> ss;
+      std::vector<int> wfrom, wn;
+      for (int f = f0; f < f1; f++) {
+        if (cfg.reset) base_reset(fw[f].profile); else std::memcpy(fw[f].profile, cur, sizeof(cur));
+        std::vector<double> xs(D);
+        for (int i = 0; i < D; i++) xs[i] = fw[f].profile[dims[i]];
+        ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma));
+        const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
+        wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
+      }
+      while (true) {
+        std::vector<const sac_window *> wins;
+        std::vector<int> from, nn, owner;
+        std::vector<float> bases;
+        std::vector<double> X;
+        std::vector<std::vector<std::vector<double>>> cands(ss.size());
+        for (size_t si = 0; si < ss.size(); si++) {
+          if (ss[si]->done()) continue;
+          ss[si]->propose(cands[si]);
+          for (auto &c : cands[si]) {
+            wins.push_back(reinterpret_cast<const sac_window *>(fw[f0 + si].win));
+            from.push_back(wfrom[si]); nn.push_back(wn[si]); owner.push_back((int)si);
+            bases.insert(bases.end(), fw[f0 + si].profile, fw[f0 + si].profile + kProfileSize);
+            X.insert(X.end(), c.begin(), c.end());
+          }
+        }
+        if (wins.empty()) break;
+        std::vector<double> cost(wins.size());
+        int rc = sac_eval_jobs(reinterpret_cast<sac_engine *>(e), (int)wins.size(), wins.data(), from.data(), nn.data(), bases.data(),
+                               dims.data(), D, X.data(), cfg.cost_kind, cfg.optk, cost.data());
+        if (rc) return rc;
+        size_t off = 0;
+        for (size_t si = 0; si < ss.size(); si++) {
+          if (cands[si].empty()) continue;
+          ss[si]->consume(&cost[off]);
+          off += cands[si].size();
+          if (cfg.verbose > 1)
+            std::fprintf(stderr, "  frame %d DDS %5d: %0.4f s=%0.3f\n", f0 + (int)si, ss[si]->nfunc(), ss[si]->best_cost(), ss[si]->sigma());
+        }
+      }
+      for (int f = f0; f < f1; f++) {
+        const auto &xb = ss[f - f0]->best_x();
+        for (int i = 0; i < D; i++) fw[f].profile[dims[i]] = (float)xb[i];                // libsac.cpp:418-420
+        std::memcpy(cur, fw[f].profile, sizeof(cur));
+      }
+    }
+  } else {
+    for (int f = 0; f < nframes; f++) std::memcpy(fw[f].profile, cur, sizeof(cur));
+  }
+  std::memcpy(profile_io, cur, sizeof(cur));
+
+  // ---- final pass (k=1, whole frame) for all frames in one batch, then payload emission ----
+  std::vector<Job> jobs(nframes);
+  for (int f = 0; f < nframes; f++) {
+    jobs[f].win = fw[f].win; jobs[f].from = 0; jobs[f].n = fw[f].n; jobs[f].k = 1;
+    std::memcpy(jobs[f].profile, fw[f].profile, sizeof(cur));
+  }
+  e->begin_call();
+  std::vector<int> cj, cc;
+  size_t stride;
+  int rc = e->run_predict(jobs, cj, cc, stride);
+  if (rc) return rc;
+  const int nchains = (int)cj.size();
+  SACB_CUDA(e->h_bpjobs.reserve(nchains));
+  SACB_CUDA(e->d_bpjobs.reserve(nchains));
+  SACB_CUDA(e->d_csig0.reserve((size_t)65536 * nchains));
+  std::vector<size_t> boff(nchains + 1, 0);
+  for (int c = 0; c < nchains; c++) boff[c + 1] = boff[c] + (((size_t)jobs[cj[c]].n * 4 + 1024 + 15) & ~size_t(15));
+  SACB_CUDA(e->d_bytes.reserve(boff[nchains]));
+  for (int c = 0; c < nchains; c++) {
+    BpJob &b = e->h_bpjobs.p[c];
+    std::memset(&b, 0, sizeof(b));
+    b.buf = e->d_resid.p + (size_t)c * stride; b.n = jobs[cj[c]].n; b.signed_input = 1; b.maxbpn = -1;
+    b.csig0 = e->d_csig0.p + (size_t)65536 * c; b.out = e->d_bytes.p + boff[c];
+    b.nbytes = e->d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = e->d_flags.p + nchains + c;
+  }
+  SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+  SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, nchains, 1, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+  e->launches++; e->last_launches[1]++;
+  SACB_CUDA(e->h_sums.reserve((size_t)3 * nchains));
+  SACB_CUDA(e->h_flags.reserve((size_t)2 * nchains));
+  SACB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, sizeof(int) * 2 * nchains, cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->last_ms[0] += ms; cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->last_ms[1] += ms; }
+  for (int c = 0; c < nchains; c++)
+    if (e->h_flags.p[c]) { set_error("final pass: predictor state became non-finite"); return SAC_E_UNSUPPORTED; }
+  // ---- serialise (WriteEncoded / WriteBlockHeader / EncodeProfile, libsac.cpp:507-578) ----
+  std::vector<uint8_t> payload;
+  for (int f = 0; f < nframes; f++) {
+    push32(out, (uint32_t)fw[f].n);
+    for (int i = 0; i < kProfileSize; i++) { uint32_t ix; std::memcpy(&ix, &fw[f].profile[i], 4); push32(out, ix); }
+    for (int ch = 0; ch < nch; ch++) {
+      int c = -1;
+      for (int q = 0; q < nchains; q++) if (cj[q] == f && cc[q] == ch) c = q;
+      const long long nb = e->h_sums.p[2 * nchains + c];
+      const int maxbpn = e->h_flags.p[nchains + c];
+      payload.resize((size_t)nb);
+      SACB_CUDA(cudaMemcpy(payload.data(), e->d_bytes.p + boff[c], (size_t)nb, cudaMemcpyDeviceToHost));
+      push32(out, (uint32_t)nb); push32(out, (uint32_t)fw[f].mean[ch]); push32(out, (uint32_t)fw[f].mm[2 * ch]); push32(out, (uint32_t)fw[f].mm[2 * ch + 1]);
+      push16(out, (uint16_t)(maxbpn & 0xff));
+      out.insert(out.end(), payload.begin(), payload.end());
+    }
+  }
+  return SAC_OK;
+}
+
+// one frame record -> planes (ReadEncoded, Decode, Unpredict)
+static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long len, std::vector<std::vector<int32_t>> &planes, int cap,
+                              int *n_out)
+{
+  const long long hdr = 4 + 4LL * kProfileSize;
+  if (len < hdr) { set_error("truncated frame record"); return SAC_E_FORMAT; }
+  const int n = (int)get32(in);
+  if (n <= 0 || n > cap) { set_error("frame record: bad sample count"); return SAC_E_FORMAT; }
+  float prof[kProfileSize];
+  for (int i = 0; i < kProfileSize; i++) { const uint32_t ix = get32(in + 4 + 4 * i); std::memcpy(&prof[i], &ix, 4); }
+  long long pos = hdr;
+  int32_t mean[2] = {0, 0}, mm[4] = {0, 0, 0, 0};
+  int maxbpn[2] = {0, 0};
+  long long poff[2] = {0, 0}, plen[2] = {0, 0};
+  for (int ch = 0; ch < nch; ch++) {
+    if (pos + 18 > len) { set_error("truncated block header"); return SAC_E_FORMAT; }
+    plen[ch] = get32(in + pos);
+    mean[ch] = (int32_t)get32(in + pos + 4); mm[2 * ch] = (int32_t)get32(in + pos + 8); mm[2 * ch + 1] = (int32_t)get32(in + pos + 12);
+    const uint16_t flag = get16(in + pos + 16);
+    if (flag >> 9) { set_error("sparse-pcm mapped frames are not supported"); return SAC_E_UNSUPPORTED; }
+    maxbpn[ch] = flag & 0xff;
+    pos += 18;
+    poff[ch] = pos;
+    if (pos + plen[ch] > len) { set_error("truncated payload"); return SAC_E_FORMAT; }
+    pos += plen[ch];
+  }
+  if (nch == 1) { mm[2] = mm[0]; mm[3] = mm[1]; }
+  SACB_CUDA(cudaSetDevice(e->device));
+  e->begin_call();
+  const size_t stride = ((size_t)n + 31) & ~size_t(31);
+  // device buffers: residuals (d_resid), decoded planes (d_scratch tail is not used here: separate allocation)
+  SACB_CUDA(e->d_resid.reserve(stride * 2 * nch));                 // [0,nch): residuals, [nch,2nch): decoded samples
+  SACB_CUDA(e->d_csig0.reserve((size_t)65536 * nch));
+  SACB_CUDA(e->h_bpjobs.reserve(nch));
+  SACB_CUDA(e->d_bpjobs.reserve(nch));
+  size_t bytes_need = 0;
+  for (int ch = 0; ch < nch; ch++) bytes_need += (((size_t)plen[ch] + 15) & ~size_t(15)) + stride;
+  SACB_CUDA(e->d_bytes.reserve(bytes_need + 64));
+  size_t bo = 0;
+  for (int ch = 0; ch < nch; ch++) {
+    BpJob &b = e->h_bpjobs.p[ch];
+    std::memset(&b, 0, sizeof(b));
+    b.buf = e->d_resid.p + (size_t)ch * stride; b.n = n; b.maxbpn = maxbpn[ch];
+    b.csig0 = e->d_csig0.p + (size_t)65536 * ch;
+    b.in = e->d_bytes.p + bo; b.in_len = plen[ch];
+    SACB_CUDA(cudaMemcpyAsync(e->d_bytes.p + bo, in + poff[ch], (size_t)plen[ch], cudaMemcpyHostToDevice, e->stream));
+    bo += ((size_t)plen[ch] + 15) & ~size_t(15);
+    b.msb = e->d_bytes.p + bo;
+    bo += stride;
+  }
+  SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob) * nch, cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+  SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, nch, 2, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+  e->launches++; e->last_launches[1]++;
+  // ---- predictor in decode direction: the two channels are coupled through progress counters ----
+  const HostParam hp = map_profile(prof);
+  SACB_CUDA(e->h_descs.reserve(nch));
+  SACB_CUDA(e->d_descs.reserve(nch));
+  SACB_CUDA(e->d_flags.reserve(8));
+  SACB_CUDA(e->d_sums.reserve(8));
+  SACB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, sizeof(int) * 8, e->stream));
+  long long soff[3] = {0, 0, 0};
+  for (int cc = 0; cc < nch; cc++) soff[cc + 1] = soff[cc] + ((chain_scratch_doubles(hp, cc, nch) + 1) & ~1LL);
+  SACB_CUDA(e->d_scratch.reserve((size_t)soff[nch]));
+  int32_t *dplanes[2] = {e->d_resid.p + (size_t)nch * stride, e->d_resid.p + (size_t)(nch + 1) * stride};
+  for (int cc = 0; cc < nch; cc++) {
+    ChainDesc &d = e->h_descs.p[cc];
+    const int32_t *cpl[2] = {dplanes[0], dplanes[1]};
+    const int actual = fill_chain(d, hp, nch, cc, 1, cpl, 0, n, mm);
+    d.own_out = dplanes[actual];
+    d.err_in = e->d_resid.p + (size_t)actual * stride;
+    d.resid = nullptr;
+    d.scratch = e->d_scratch.p + soff[cc]; d.scratch_doubles = soff[cc + 1] - soff[cc];
+    d.l1sum = nullptr; d.sqsum = nullptr; d.flags = e->d_flags.p + cc;
+    d.progress = e->d_flags.p + 4 + cc;
+    d.wait_ctr = nullptr; d.wait_add = 0;
+    if (nch == 2 && d.lenB > 0) {
+      d.wait_ctr = e->d_flags.p + 4 + (1 - cc);
+      d.wait_add = cc == 0 ? -(std::max(hp.nS1, 1) - 1) : hp.nS1;
+    }
+  }
+  SACB_CUDA(cudaMemcpyAsync(e->d_descs.p, e->h_descs.p, sizeof(ChainDesc) * nch, cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+  SACB_CUDA(launch_predictor(e->d_descs.p, nch, e->smem_bytes, true, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+  e->launches++; e->last_launches[0]++;
+  for (int ch = 0; ch < nch; ch++) {
+    planes[ch].resize(n);
+    SACB_CUDA(cudaMemcpyAsync(planes[ch].data(), dplanes[ch], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+  }
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->last_ms[0] += ms; cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->last_ms[1] += ms; }
+  for (int ch = 0; ch < nch; ch++)
+    if (mean[ch] != 0) for (auto &v : planes[ch]) v += mean[ch];     // libsac.cpp:194-198
+  *n_out = n;
+  return pos;
+}
+
+// =====================================================================================================================
+// files
+// =====================================================================================================================
+static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out, sac_file_stats *st)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  WavInfo wi;
+  int rc = wav_parse(wav, wav_len, wi);
+  if (rc) return rc;
+  if (!(wi.bits <= 24 && (wi.nch == 1 || wi.nch == 2)) || wi.blockalign <= 0 || wi.blockalign % wi.nch) {
+    set_error("unsupported input format: must be 1-16 bit, mono/stereo, pcm");          // cmdline.cpp:253-262
+    return SAC_E_UNSUPPORTED;
+  }
+  const int max_framesize = cfg.max_framelen * wi.samplerate;
+  if (max_framesize <= 0) { set_error("bad frame length"); return SAC_E_ARG; }
+  // ---- .sac header (sac.cpp:15-38) + MD5 placeholder ----
+  out.clear();
+  out.push_back('S'); out.push_back('A'); out.push_back('C'); out.push_back('2');
+  push16(out, (uint16_t)wi.nch); push32(out, (uint32_t)wi.samplerate); push16(out, (uint16_t)wi.bits); push32(out, wi.numsamples);
+  out.push_back((uint8_t)cfg.max_framelen); out.push_back(0);
+  push32(out, wi.metadatasize());
+  pack_metadata(wi, out);
+  const size_t md5pos = out.size();
+  out.resize(out.size() + 16, 0);
+  // ---- samples ----
+  const uint8_t *pcm = wav + wi.data_pos;
+  const size_t pcm_bytes = (size_t)wi.numsamples * wi.blockalign;
+  Md5 md5;
+  md5.update(pcm, pcm_bytes);
+  const int nframes = (int)((wi.numsamples + (uint32_t)max_framesize - 1) / (uint32_t)max_framesize);
+  std::vector<std::vector<int32_t>> store((size_t)nframes * wi.nch);
+  std::vector<const int32_t *> ptrs((size_t)nframes * wi.nch);
+  std::vector<int> ns(nframes);
+  for (int f = 0; f < nframes; f++) {
+    const int first = f * max_framesize;
+    ns[f] = (int)std::min<uint32_t>((uint32_t)max_framesize, wi.numsamples - (uint32_t)first);
+    std::vector<std::vector<int32_t>> pl(wi.nch, std::vector<int32_t>(ns[f]));
+    wav_unpack(wi, pcm, first, ns[f], pl);
+    for (int ch = 0; ch < wi.nch; ch++) { store[(size_t)f * wi.nch + ch] = std::move(pl[ch]); ptrs[(size_t)f * wi.nch + ch] = store[(size_t)f * wi.nch + ch].data(); }
+  }
+  float prof[kProfileSize];
+  for (int i = 0; i < kProfileSize; i++) prof[i] = kBaseProfile[i][2];
+  if (nframes > 0) {
+    rc = frames_encode(e, cfg, wi.nch, max_framesize, nframes, ptrs.data(), ns.data(), prof, out);
+    if (rc) return rc;
+  }
+  uint8_t dig[16];
+  md5.final(dig);
+  std::memcpy(out.data() + md5pos, dig, 16);
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->in_bytes = (long long)wav_len; st->out_bytes = (long long)out.size(); st->numsamples = (int)wi.numsamples; st->nch = wi.nch;
+    st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, dig, 16); st->md5_ok = 1;
+    st->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return SAC_OK;
+}
+
+static int decode_image(Engine *e, const uint8_t *sac, size_t len, std::vector<uint8_t> &out, sac_file_stats *st)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  if (len < 22 + 16 || !(sac[0] == 'S' && sac[1] == 'A' && sac[2] == 'C' && sac[3] == '2')) { set_error("input is not a valid .sac file"); return SAC_E_FORMAT; }
+  WavInfo wi;
+  wi.nch = get16(sac + 4); wi.samplerate = (int)get32(sac + 6); wi.bits = get16(sac + 10); wi.numsamples = get32(sac + 12);
+  const int max_framelen = sac[16];
+  const uint32_t mdsize = get32(sac + 18);
+  if (22 + (size_t)mdsize + 16 > len || wi.nch < 1 || wi.nch > 2) { set_error("corrupt .sac header"); return SAC_E_FORMAT; }
+  if (unpack_metadata(sac + 22, mdsize, wi)) { set_error("unpackmetadata mismatch"); return SAC_E_FORMAT; }
+  size_t pos = 22 + mdsize;
+  uint8_t want[16];
+  std::memcpy(want, sac + pos, 16);
+  pos += 16;
+  const int csize = (wi.bits + 7) / 8;                                // Wav(AudioFile&) ctor (wav.cpp:61-70)
+  wi.blockalign = wi.nch * csize;
+  const int max_framesize = max_framelen * wi.samplerate;
+  // ---- WAV header chunks up to and including 'data' (Wav::WriteHeader, wav.cpp:265-281) ----
+  out.clear();
+  size_t chunkpos = 0;
+  auto write_header = [&]() {
+    while (chunkpos < wi.chunks.size()) {
+      const WavChunk &c = wi.chunks[chunkpos++];
+      push32(out, c.id); push32(out, c.csize);
+      if (c.id == kDATA) break;
+      out.insert(out.end(), c.data.begin(), c.data.end());
+    }
+  };
+  write_header();
+  Md5 md5;
+  long long todo = wi.numsamples, data_bytes = 0;
+  int nframes = 0;
+  std::vector<std::vector<int32_t>> planes(wi.nch);
+  while (todo > 0) {
+    int n = 0;
+    const long long used = frame_decode(e, wi.nch, sac + pos, (long long)(len - pos), planes, max_framesize, &n);
+    if (used < 0) return (int)used;
+    pos += (size_t)used;
+    const size_t o0 = out.size();
+    wav_pack(wi, planes, n, out);
+    md5.update(out.data() + o0, out.size() - o0);
+    data_bytes += (long long)(out.size() - o0);
+    todo -= n;
+    nframes++;
+  }
+  if (data_bytes & 1) out.push_back(0);                               // libsac.cpp:880-881
+  write_header();
+  uint8_t dig[16];
+  md5.final(dig);
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->in_bytes = (long long)len; st->out_bytes = (long long)out.size(); st->numsamples = (int)wi.numsamples; st->nch = wi.nch;
+    st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, dig, 16);
+    st->md5_ok = std::memcmp(dig, want, 16) == 0;
+    st->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return SAC_OK;
+}
+
+static int read_file(const char *path, std::vector<uint8_t> &buf)
+{
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { set_error(std::string("could not open ") + path); return SAC_E_IO; }
+  f.seekg(0, std::ios::end);
+  const std::streamoff sz = f.tellg();
+  f.seekg(0);
+  buf.resize((size_t)sz);
+  if (sz) f.read(reinterpret_cast<char *>(buf.data()), sz);
+  return f ? SAC_OK : SAC_E_IO;
+}
+static int write_file(const char *path, const std::vector<uint8_t> &buf)
+{
+  std::ofstream f(path, std::ios::binary);
+  if (!f) { set_error(std::string("could not create ") + path); return SAC_E_IO; }
+  f.write(reinterpret_cast<const char *>(buf.data()), (std::streamsize)buf.size());
+  return f ? SAC_OK : SAC_E_IO;
+}
+
+} // namespace sacb
+
+using namespace sacb;
+
+extern "C" {
+
+double sac_dds_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
+                   double sigma_init, sac_eval_fn eval, void *user, double *xbest)
+{
+  if (D <= 0 || !xmin || !xmax || !xstart || !eval || nfunc_max < 1) { set_error("sac_dds_run: bad argument"); return std::numeric_limits<double>::quiet_NaN(); }
+  DdsSearch s(D, xmin, xmax, xstart, nfunc_max, num_threads, sigma_init);
+  std::vector<std::vector<double>> cands;
+  std::vector<double> X, cost;
+  do {
+    s.propose(cands);
+    X.clear();
+    for (auto &c : cands) X.insert(X.end(), c.begin(), c.end());
+    cost.assign(cands.size(), 0.0);
+    if (eval(X.data(), (int)cands.size(), D, cost.data(), user)) { set_error("sac_dds_run: evaluator aborted"); break; }
+    s.consume(cost.data());
+  } while (!s.done());
+  if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);
+  return s.best_cost();
+}
+
+void sac_cfg_default(sac_cfg *c)
+{
+  std::memset(c, 0, sizeof(*c));
+  c->optimize = 0; c->fraction = 0; c->maxnfunc = 0; c->num_threads = 0; c->sigma = 0.2; c->optk = 4;
+  c->cost_kind = SAC_COST_ENTROPY; c->reset = 0; c->zero_mean = 1; c->sparse_pcm = 1; c->max_framelen = 20; c->adapt_block = 1;
+  c->frame_parallel = 0; c->verbose = 0;
+}
+int sac_cfg_preset(sac_cfg *c, const char *name)                        // cmdline.cpp:127-156
+{
+  std::string s(name ? name : "");
+  for (auto &ch : s) ch = (char)std::tolower(ch);
+  if (s == "normal") { c->optimize = 0; }
+  else if (s == "high") { c->optimize = 1; c->fraction = 0.1; c->maxnfunc = 100; c->sigma = 0.20; }
+  else if (s == "veryhigh") { c->optimize = 1; c->fraction = 0.2; c->maxnfunc = 300; c->sigma = 0.25; }
+  else if (s == "extrahigh") { c->optimize = 1; c->fraction = 0.2; c->maxnfunc = 600; c->sigma = 0.25; }
+  else if (s == "best") { c->optimize = 1; c->fraction = 0.50; c->maxnfunc = 1000; c->sigma = 0.25; c->cost_kind = SAC_COST_BITPLANE; }
+  else if (s == "insane") { c->optimize = 1; c->fraction = 0.50; c->maxnfunc = 1500; c->sigma = 0.25; c->cost_kind = SAC_COST_BITPLANE; }
+  else { set_error("unknown preset"); return SAC_E_ARG; }
+  return SAC_OK;
+}
+
+int sac_frames_encode(sac_engine *h, const sac_cfg *cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
+                      const int *numsamples, float *profile_io, uint8_t *out, long long cap, long long *out_len)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !cfg || nch < 1 || nch > 2 || nframes <= 0 || !planes || !numsamples || !profile_io || !out_len) { set_error("sac_frames_encode: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> buf;
+  int rc = frames_encode(e, *cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, buf);
+  if (rc) return rc;
+  *out_len = (long long)buf.size();
+  if ((long long)buf.size() > cap || !out) { set_error("output buffer too small"); return SAC_E_ARG; }
+  std::memcpy(out, buf.data(), buf.size());
+  return SAC_OK;
+}
+
+long long sac_frame_decode(sac_engine *h, int nch, const uint8_t *in, long long len, int32_t *const *planes_out, int cap_samples, int *numsamples)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || nch < 1 || nch > 2 || !in || !planes_out || !numsamples) { set_error("sac_frame_decode: bad argument"); return SAC_E_ARG; }
+  std::vector<std::vector<int32_t>> planes(nch);
+  int n = 0;
+  const long long used = frame_decode(e, nch, in, len, planes, cap_samples, &n);
+  if (used < 0) return used;
+  for (int ch = 0; ch < nch; ch++) std::memcpy(planes_out[ch], planes[ch].data(), sizeof(int32_t) * (size_t)n);
+  *numsamples = n;
+  return used;
+}
+
+int sac_encode_memory(sac_engine *h, const sac_cfg *cfg, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap,
+                      long long *out_len, sac_file_stats *st)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !cfg || !wav || wav_len <= 0 || !out_len) { set_error("sac_encode_memory: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> buf;
+  int rc = encode_image(e, *cfg, wav, (size_t)wav_len, buf, st);
+  if (rc) return rc;
+  *out_len = (long long)buf.size();
+  if (!out || (long long)buf.size() > cap) { set_error("output buffer too small"); return SAC_E_ARG; }
+  std::memcpy(out, buf.data(), buf.size());
+  return SAC_OK;
+}
+int sac_decode_memory(sac_engine *h, const uint8_t *sac, long long sac_len, uint8_t *out, long long cap, long long *out_len, sac_file_stats *st)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !sac || sac_len <= 0 || !out_len) { set_error("sac_decode_memory: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> buf;
+  int rc = decode_image(e, sac, (size_t)sac_len, buf, st);
+  if (rc) return rc;
+  *out_len = (long long)buf.size();
+  if (!out || (long long)buf.size() > cap) { set_error("output buffer too small"); return SAC_E_ARG; }
+  std::memcpy(out, buf.data(), buf.size());
+  return SAC_OK;
+}
+int sac_encode_file(sac_engine *h, const sac_cfg *cfg, const char *wav_path, const char *sac_path, sac_file_stats *st)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !cfg || !wav_path || !sac_path) { set_error("sac_encode_file: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> in, out;
+  int rc = read_file(wav_path, in);
+  if (rc) return rc;
+  rc = encode_image(e, *cfg, in.data(), in.size(), out, st);
+  if (rc) return rc;
+  return write_file(sac_path, out);
+}
+int sac_decode_file(sac_engine *h, const char *sac_path, const char *wav_path, sac_file_stats *st)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !sac_path || !wav_path) { set_error("sac_decode_file: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> in, out;
+  int rc = read_file(sac_path, in);
+  if (rc) return rc;
+  rc = decode_image(e, in.data(), in.size(), out, st);
+  if (rc) return rc;
+  return write_file(wav_path, out);
+}
+
+} // extern "C"

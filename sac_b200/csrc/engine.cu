@@ -1,0 +1,450 @@
+// engine.cu -- per-GPU engine: pools in HBM, descriptor building (FrameCoder::SetParam), batched kernel launches,
+// and the compute half of the C ABI (include/sac_b200.h).
+#include "engine.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+namespace sacb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+  set_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+  return SAC_E_CUDA;
+}
+
+// SacProfile::LoadBaseProfile (profile.cpp:3-89): {vmin, vmax, vdef} per coefficient index
+const float kBaseProfile[kProfileSize][3] = {
+    {0.99f, 0.9999f, 0.998f}, {1.0f, 100.0f, 25.0f},    {0.001f, 1.0f, 0.1f},      {0.001f, 1.0f, 0.12f},    {0.001f, 1.0f, 0.06f},
+    {0.001f, 1.0f, 0.04f},    {0.98f, 1.0f, 1.0f},      {0.0f, 1.0f, 0.8f},        {0.0f, 1.0f, 0.8f},       {0.0f, 32.0f, 0.0f},
+    {0.0005f, 0.05f, 0.005f}, {0.8f, 0.9999f, 0.95f},   {0.99f, 0.9999f, 0.998f},  {1.0f, 100.0f, 25.0f},    {0.001f, 1.0f, 0.1f},
+    {0.001f, 1.0f, 0.12f},    {0.001f, 1.0f, 0.06f},    {0.001f, 1.0f, 0.04f},     {0.98f, 1.0f, 1.0f},      {0.0f, 1.0f, 0.8f},
+    {0.0f, 1.0f, 0.8f},       {0.0f, 1.0f, 0.8f},       {0.0005f, 0.05f, 0.005f},  {0.8f, 0.9999f, 0.95f},   {4.0f, 32.0f, 16.0f},
+    {4.0f, 32.0f, 16.0f},     {0.0f, 32.0f, 8.0f},      {-32.0f, 32.0f, 8.0f},     {256.0f, 8192.0f, 1280.0f}, {32.0f, 4096.0f, 256.0f},
+    {4.0f, 2048.0f, 32.0f},   {256.0f, 8192.0f, 1280.0f}, {32.0f, 4096.0f, 256.0f}, {4.0f, 2048.0f, 32.0f},  {0.0f, 1.0f, 0.5f},
+    {0.1f, 2.0f, 0.8f},       {0.1f, 10.0f, 2.0f},      {2.0f, 1024.0f, 4.0f},     {2.0f, 1024.0f, 4.0f},    {0.98f, 1.0f, 1.0f},
+    {0.98f, 1.0f, 1.0f},      {1.0f, 10.0f, 4.0f},      {0.1f, 10.0f, 5.0f},       {0.001f, 0.005f, 0.0015f}, {0.001f, 0.005f, 0.0015f},
+    {4.0f, 10.0f, 5.0f},      {0.98f, 1.0f, 1.0f},      {0.98f, 1.0f, 1.0f},       {0.98f, 1.0f, 1.0f},      {0.98f, 1.0f, 1.0f},
+    {0.0f, 1.0f, 0.8f},       {0.0f, 1.0f, 0.8f},       {0.0f, 1.0f, 0.8f},        {0.0f, 1.0f, 0.5f},       {0.1f, 2.0f, 0.8f},
+    {0.1f, 10.0f, 2.0f},      {0.0f, 0.5f, 0.1f},       {0.0f, 0.5f, 0.1f}};
+
+// FrameCoder::SetParam (libsac.cpp:37-92). Values are clamped to the structural limits of the kernels (the DDS box
+// keeps them inside anyway: profile.cpp:47-53,66-67).
+HostParam map_profile(const float *g)
+{
+  HostParam p;
+  auto G = [&](int i) { return (double)g[i]; };
+  auto R = [&](int i) { return (int)std::round(G(i)); };
+  const int in0[4] = {28, 29, 30, 37}, in1[4] = {31, 32, 33, 38};
+  const int imu0[4] = {2, 3, 4, 5}, imu1[4] = {14, 15, 16, 17};
+  const int imd0[4] = {6, 39, 46, 47}, imd1[4] = {18, 40, 48, 49};
+  const int ipd0[4] = {7, 8, 50, 51}, ipd1[4] = {19, 20, 21, 52};
+  for (int i = 0; i < 4; i++) {
+    p.vn[0][i] = std::clamp(R(in0[i]), 1, 8192); p.vn[1][i] = std::clamp(R(in1[i]), 1, 8192);
+    p.vmu[0][i] = G(imu0[i]) / double(p.vn[0][i]); p.vmu[1][i] = G(imu1[i]) / double(p.vn[1][i]);
+    p.vmudecay[0][i] = G(imd0[i]); p.vmudecay[1][i] = G(imd1[i]);
+    p.vpowdecay[0][i] = G(ipd0[i]); p.vpowdecay[1][i] = G(ipd1[i]);
+  }
+  p.lambda[0] = G(0); p.ols_nu[0] = G(1); p.mu_mix[0] = G(10); p.mu_mix_beta[0] = G(11);
+  p.lambda[1] = G(12); p.ols_nu[1] = G(13); p.mu_mix[1] = G(22); p.mu_mix_beta[1] = G(23);
+  p.nA = std::clamp(R(24), 1, 32); p.nB = std::clamp(R(25), 1, 32); p.nS0 = std::clamp(R(26), 0, 32);
+  p.nS1 = std::clamp(R(27), -32, 32); p.nM0 = std::clamp(R(9), 0, 32);
+  p.beta_sum[0] = G(34); p.beta_pow[0] = G(35); p.beta_add[0] = G(36);
+  p.beta_sum[1] = G(53); p.beta_pow[1] = G(54); p.beta_add[1] = G(55);
+  p.proj_alpha[0] = G(56); p.proj_alpha[1] = G(57);
+  p.lm_n = std::clamp(R(41), 1, (int)kMaxRls); p.lm_alpha = G(42);
+  p.bias_mu[0] = G(43); p.bias_mu[1] = G(44);
+  p.bias_scale = std::clamp(R(45), 0, 30);
+  p.ch_ref = 0;
+  if (p.nS1 < 0) { p.nS1 = -p.nS1; p.ch_ref = 1; }
+  return p;
+}
+
+static int ols_order(const HostParam &hp, int cc) { return cc == 0 ? hp.nA + hp.nM0 : hp.nB + hp.nS0 + hp.nS1; }
+
+long long chain_scratch_doubles(const HostParam &hp, int cc, int)
+{
+  long long t = 0;
+  for (int s = 0; s < 4; s++) t += 4LL * hp.vn[cc][s] + 1;
+  const long long n = ols_order(hp, cc);
+  t += (n + 1) * (n + 2);
+  return t + 8;
+}
+
+int fill_chain(ChainDesc &d, const HostParam &hp, int nch, int cc, int k, const int32_t *const *planes, int from, int n,
+               const int32_t *mm)
+{
+  std::memset(&d, 0, sizeof(d));
+  int actual;
+  if (nch == 1) {
+    actual = 0;
+    d.own = planes[0] + from; d.other = planes[0] + from;
+    d.lenA = hp.nA; d.lenB = hp.nM0; d.lagB = 0; d.minB = 0; d.backB = hp.nM0;
+  } else if (cc == 0) {
+    actual = hp.ch_ref;
+    d.own = planes[actual] + from; d.other = planes[1 - actual] + from;
+    d.lenA = hp.nA; d.lenB = hp.nM0; d.lagB = std::max(hp.nS1, 1) - 1; d.minB = 0; d.backB = hp.nM0;
+  } else {
+    actual = 1 - hp.ch_ref;
+    d.own = planes[actual] + from; d.other = planes[1 - actual] + from;
+    d.lenA = hp.nB; d.lenB = hp.nS0 + hp.nS1; d.lagB = 0; d.minB = -(1 << 30); d.backB = hp.nS0;
+  }
+  d.n = n;
+  d.k = k;
+  d.lambda = hp.lambda[cc];
+  d.nu = (1.0 - hp.lambda[cc]) * hp.ols_nu[cc];                      // ols.cpp:11
+  d.beta_sum = hp.beta_sum[cc]; d.beta_pow = hp.beta_pow[cc]; d.beta_add = hp.beta_add[cc];
+  for (int s = 0; s < 4; s++) {
+    d.vn[s] = hp.vn[cc][s]; d.vmu[s] = hp.vmu[cc][s]; d.vmudecay[s] = hp.vmudecay[cc][s]; d.vpowdecay[s] = hp.vpowdecay[cc][s];
+  }
+  d.mu_mix = hp.mu_mix[cc]; d.mix_beta = hp.mu_mix_beta[cc];
+  d.lm_n = hp.lm_n; d.lm_gamma = hp.lm_alpha; d.proj_alpha = hp.proj_alpha[cc];
+  // Cascade ranges follow the coded-channel index, residual clamps the actual channel (libsac.cpp:98-102,106)
+  const int ri = (nch == 2) ? cc : 0;
+  d.casc_lo = (double)mm[2 * ri]; d.casc_hi = (double)mm[2 * ri + 1];
+  d.clamp_lo = mm[2 * actual]; d.clamp_hi = mm[2 * actual + 1];
+  d.bias_mu = hp.bias_mu[cc]; d.bias_nscale = 1 << hp.bias_scale;
+  return actual;
+}
+
+// ---- Engine ----------------------------------------------------------------------------------------------------------
+int Engine::init(int dev)
+{
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+    set_error("no CUDA device visible: libsac_b200 has no CPU fallback");
+    return SAC_E_NODEVICE;
+  }
+  if (dev < 0 || dev >= cnt) { set_error("device index out of range"); return SAC_E_ARG; }
+  device = dev;
+  SACB_CUDA(cudaSetDevice(dev));
+  SACB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
+  if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
+  SACB_CUDA(bt.init(stream));
+  return SAC_OK;
+}
+void Engine::destroy()
+{
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  d_descs.release(); h_descs.release(); d_scratch.release(); d_resid.release(); d_sums.release(); d_flags.release();
+  h_sums.release(); h_flags.release(); d_bpjobs.release(); h_bpjobs.release(); d_csig0.release(); d_hist.release();
+  d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release();
+  bt.destroy();
+  for (auto &e : ev) if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+}
+void Engine::begin_call()
+{
+  for (int i = 0; i < 3; i++) { last_ms[i] = 0; last_launches[i] = 0; }
+}
+
+int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride)
+{
+  SACB_CUDA(cudaSetDevice(device));
+  chain_job.clear(); chain_ch.clear();
+  size_t maxn = 0;
+  int nchains = 0;
+  for (auto &j : jobs) { nchains += j.win->nch; maxn = std::max(maxn, (size_t)j.n); }
+  stride = (maxn + 31) & ~size_t(31);
+  SACB_CUDA(h_descs.reserve(nchains));
+  SACB_CUDA(d_descs.reserve(nchains));
+  SACB_CUDA(d_resid.reserve(stride * nchains));
+  SACB_CUDA(d_sums.reserve((size_t)3 * nchains));
+  SACB_CUDA(d_flags.reserve((size_t)4 * nchains));
+  // scratch offsets
+  std::vector<long long> soff(nchains + 1, 0);
+  std::vector<HostParam> hps(jobs.size());
+  int c = 0;
+  for (size_t ji = 0; ji < jobs.size(); ji++) {
+    const Job &j = jobs[ji];
+    if (j.from < 0 || j.n <= 0 || j.from + j.n > j.win->numsamples) { set_error("window range outside the frame"); return SAC_E_ARG; }
+    hps[ji] = map_profile(j.profile);
+    for (int cc = 0; cc < j.win->nch; cc++, c++) soff[c + 1] = soff[c] + ((chain_scratch_doubles(hps[ji], cc, j.win->nch) + 1) & ~1LL);
+  }
+  SACB_CUDA(d_scratch.reserve((size_t)soff[nchains]));
+  c = 0;
+  for (size_t ji = 0; ji < jobs.size(); ji++) {
+    const Job &j = jobs[ji];
+    for (int cc = 0; cc < j.win->nch; cc++, c++) {
+      ChainDesc &d = h_descs.p[c];
+      const int actual = fill_chain(d, hps[ji], j.win->nch, cc, j.k, j.win->d_planes, j.from, j.n, j.win->minmax);
+      d.resid = d_resid.p + (size_t)c * stride;
+      d.scratch = d_scratch.p + soff[c];
+      d.scratch_doubles = soff[c + 1] - soff[c];
+      d.l1sum = d_sums.p + c; d.sqsum = d_sums.p + nchains + c; d.flags = d_flags.p + c;
+      chain_job.push_back((int)ji); chain_ch.push_back(actual);
+    }
+  }
+  SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
+  SACB_CUDA(cudaEventRecord(ev[0], stream));
+  SACB_CUDA(launch_predictor(d_descs.p, nchains, smem_bytes, false, stream));
+  SACB_CUDA(cudaEventRecord(ev[1], stream));
+  launches++; last_launches[0]++;
+  return SAC_OK;
+}
+
+int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vector<int> &chain_job, const std::vector<int> &chain_ch,
+                     size_t stride, double *cost)
+{
+  const int nchains = (int)chain_job.size();
+  SACB_CUDA(h_sums.reserve((size_t)3 * nchains));
+  SACB_CUDA(h_flags.reserve((size_t)2 * nchains));
+  SACB_CUDA(h_cost.reserve(nchains));
+  SACB_CUDA(d_cost.reserve(nchains));
+  std::vector<double> ccost(nchains, 0.0);
+  SACB_CUDA(cudaEventRecord(ev[2], stream));
+  if (cost_kind == SAC_COST_ENTROPY || cost_kind == SAC_COST_GOLOMB) {
+    // ns / ranges ride in the flags pool's second half
+    std::vector<int> meta(2 * nchains);
+    size_t maxbins = 0;
+    for (int c = 0; c < nchains; c++) {
+      const Job &j = jobs[chain_job[c]];
+      meta[c] = j.n;
+      const int ch = chain_ch[c];
+      const long long R = (long long)j.win->minmax[2 * ch + 1] - (long long)j.win->minmax[2 * ch];
+      if (cost_kind == SAC_COST_ENTROPY && R > (1 << 20)) { set_error("entropy cost: residual range above 2^20 not supported"); return SAC_E_UNSUPPORTED; }
+      meta[nchains + c] = (int)std::max<long long>(R, 1);
+      maxbins = std::max(maxbins, (size_t)(2 * meta[nchains + c] + 1));
+    }
+    DevBuf<int> &dm = d_flags;                                      // [0,n) flags, [2n,3n) ns, [3n,4n) ranges (reserved in run_predict)
+    SACB_CUDA(cudaMemcpyAsync(dm.p + 2 * nchains, meta.data(), sizeof(int) * 2 * nchains, cudaMemcpyHostToDevice, stream));
+    if (cost_kind == SAC_COST_ENTROPY) {
+      const size_t hs = (maxbins + 31) & ~size_t(31);
+      SACB_CUDA(d_hist.reserve(hs * nchains));
+      SACB_CUDA(launch_entropy(d_resid.p, stride, dm.p + 2 * nchains, dm.p + 3 * nchains, nchains, d_hist.p, hs, d_cost.p, stream));
+    } else {
+      SACB_CUDA(launch_golomb(d_resid.p, stride, dm.p + 2 * nchains, nchains, d_cost.p, stream));
+    }
+    launches++; last_launches[2]++;
+    SACB_CUDA(cudaMemcpyAsync(h_cost.p, d_cost.p, sizeof(double) * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaEventRecord(ev[3], stream));
+    SACB_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < nchains; c++) ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : h_cost.p[c];
+    float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[2] += ms;
+  } else if (cost_kind == SAC_COST_BITPLANE) {
+    SACB_CUDA(h_bpjobs.reserve(nchains));
+    SACB_CUDA(d_bpjobs.reserve(nchains));
+    SACB_CUDA(d_csig0.reserve((size_t)65536 * nchains));
+    for (int c = 0; c < nchains; c++) {
+      BpJob &b = h_bpjobs.p[c];
+      std::memset(&b, 0, sizeof(b));
+      b.buf = d_resid.p + (size_t)c * stride; b.n = jobs[chain_job[c]].n; b.signed_input = 1; b.maxbpn = -1;
+      b.csig0 = d_csig0.p + (size_t)65536 * c; b.nbytes = d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = nullptr;
+    }
+    SACB_CUDA(cudaMemcpyAsync(d_bpjobs.p, h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, stream));
+    SACB_CUDA(launch_bitplane(bt, d_bpjobs.p, nchains, 0, stream));
+    launches++; last_launches[1]++;
+    SACB_CUDA(cudaEventRecord(ev[3], stream));
+    SACB_CUDA(cudaMemcpyAsync(h_sums.p, d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < nchains; c++)
+      ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : (double)h_sums.p[2 * nchains + c];
+    float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[1] += ms;
+  } else if (cost_kind == SAC_COST_L1 || cost_kind == SAC_COST_RMS) {
+    SACB_CUDA(cudaMemcpyAsync(h_sums.p, d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
+    SACB_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < nchains; c++) {
+      const double n = (double)jobs[chain_job[c]].n;
+      double v = cost_kind == SAC_COST_L1 ? h_sums.p[c] / n : std::sqrt(h_sums.p[nchains + c] / n);   // cost.h:15-41
+      ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : v;
+    }
+  } else { set_error("unknown cost kind"); return SAC_E_ARG; }
+  { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms; }
+  for (size_t j = 0; j < jobs.size(); j++) cost[j] = 0.0;
+  // sum over channels (FrameCoder::GetCost, libsac.cpp:358-361; a two-term sum is order-independent)
+  for (int c = 0; c < nchains; c++) cost[chain_job[c]] += ccost[c];
+  return SAC_OK;
+}
+
+} // namespace sacb
+
+// =====================================================================================================================
+using namespace sacb;
+
+extern "C" {
+
+const char *sac_version(void) { return "sac_b200 0.1 (bitstream: Sac v0.7.25 container, canonical-arithmetic model)"; }
+const char *sac_last_error(void) { return g_err.c_str(); }
+int sac_device_count(void)
+{
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+  return c;
+}
+
+sac_engine *sac_engine_create(int device)
+{
+  Engine *e = new Engine();
+  if (e->init(device) != SAC_OK) { delete e; return nullptr; }
+  return reinterpret_cast<sac_engine *>(e);
+}
+void sac_engine_destroy(sac_engine *h)
+{
+  if (!h) return;
+  Engine *e = reinterpret_cast<Engine *>(h);
+  e->destroy();
+  delete e;
+}
+long long sac_engine_launches(const sac_engine *h) { return reinterpret_cast<const Engine *>(h)->launches; }
+void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_launches)
+{
+  const Engine *e = reinterpret_cast<const Engine *>(h);
+  for (int i = 0; i < 3; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
+}
+
+int sac_base_profile(float *vmin, float *vmax, float *vdef)
+{
+  for (int i = 0; i < kProfileSize; i++) {
+    if (vmin) vmin[i] = kBaseProfile[i][0];
+    if (vmax) vmax[i] = kBaseProfile[i][1];
+    if (vdef) vdef[i] = kBaseProfile[i][2];
+  }
+  return kProfileSize;
+}
+
+sac_window *sac_window_create(sac_engine *h, int nch, const int32_t *const *planes, int numsamples, const int32_t *minmax)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || nch < 1 || nch > 2 || numsamples <= 0 || !planes || !minmax) { set_error("sac_window_create: bad argument"); return nullptr; }
+  cudaSetDevice(e->device);
+  Window *w = new Window();
+  w->eng = e; w->nch = nch; w->numsamples = numsamples;
+  w->d_planes[0] = w->d_planes[1] = nullptr;
+  for (int i = 0; i < 2 * nch; i++) w->minmax[i] = minmax[i];
+  if (nch == 1) { w->minmax[2] = minmax[0]; w->minmax[3] = minmax[1]; }
+  if (e->h_stage.reserve(numsamples) != cudaSuccess) { delete w; set_error("pinned staging allocation failed"); return nullptr; }
+  for (int ch = 0; ch < nch; ch++) {
+    if (cudaMalloc(&w->d_planes[ch], sizeof(int32_t) * (size_t)numsamples) != cudaSuccess) { set_error("HBM allocation failed"); sac_window_destroy(reinterpret_cast<sac_window *>(w)); return nullptr; }
+    std::memcpy(e->h_stage.p, planes[ch], sizeof(int32_t) * (size_t)numsamples);
+    cudaMemcpyAsync(w->d_planes[ch], e->h_stage.p, sizeof(int32_t) * (size_t)numsamples, cudaMemcpyHostToDevice, e->stream);
+    cudaStreamSynchronize(e->stream);
+  }
+  return reinterpret_cast<sac_window *>(w);
+}
+void sac_window_destroy(sac_window *h)
+{
+  Window *w = reinterpret_cast<Window *>(h);
+  if (!w) return;
+  cudaSetDevice(w->eng->device);
+  for (int ch = 0; ch < 2; ch++) if (w->d_planes[ch]) cudaFree(w->d_planes[ch]);
+  delete w;
+}
+
+int sac_predict(sac_engine *h, const sac_window *wh, const float *profiles, int P, int from, int n, int k, int32_t *resid, int *flags)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  const Window *w = reinterpret_cast<const Window *>(wh);
+  if (!e || !w || !profiles || P <= 0 || !resid || k < 1) { set_error("sac_predict: bad argument"); return SAC_E_ARG; }
+  e->begin_call();
+  std::vector<Job> jobs(P);
+  for (int p = 0; p < P; p++) {
+    jobs[p].win = w; jobs[p].from = from; jobs[p].n = n; jobs[p].k = k;
+    std::memcpy(jobs[p].profile, profiles + (size_t)p * kProfileSize, sizeof(float) * kProfileSize);
+  }
+  std::vector<int> cj, cc;
+  size_t stride;
+  int rc = e->run_predict(jobs, cj, cc, stride);
+  if (rc) return rc;
+  const int nchains = (int)cj.size();
+  SACB_CUDA(e->h_flags.reserve((size_t)2 * nchains));
+  SACB_CUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, e->stream));
+  for (int c = 0; c < nchains; c++) {
+    int32_t *dst = resid + ((size_t)cj[c] * w->nch + cc[c]) * n;
+    SACB_CUDA(cudaMemcpyAsync(dst, e->d_resid.p + (size_t)c * stride, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+  }
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->last_ms[0] += ms; }
+  if (flags) {
+    for (int p = 0; p < P; p++) flags[p] = 0;
+    for (int c = 0; c < nchains; c++) flags[cj[c]] |= e->h_flags.p[c];
+  }
+  return SAC_OK;
+}
+
+int sac_eval_jobs(sac_engine *h, int njobs, const sac_window *const *wins, const int *from, const int *n, const float *bases,
+                  const int *dims, int D, const double *X, int cost_kind, int optk, double *cost)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || njobs <= 0 || !wins || !from || !n || !bases || !X || !cost || D < 0 || D > kProfileSize || optk < 1) {
+    set_error("sac_eval_jobs: bad argument");
+    return SAC_E_ARG;
+  }
+  e->begin_call();
+  std::vector<Job> jobs(njobs);
+  for (int j = 0; j < njobs; j++) {
+    jobs[j].win = reinterpret_cast<const Window *>(wins[j]);
+    if (!jobs[j].win) { set_error("sac_eval_jobs: null window"); return SAC_E_ARG; }
+    jobs[j].from = from[j]; jobs[j].n = n[j]; jobs[j].k = optk;
+    std::memcpy(jobs[j].profile, bases + (size_t)j * kProfileSize, sizeof(float) * kProfileSize);
+    for (int i = 0; i < D; i++) {
+      const int idx = dims ? dims[i] : (i < 56 ? i : -1);
+      if (idx < 0 || idx >= kProfileSize) { set_error("sac_eval_jobs: bad dimension index"); return SAC_E_ARG; }
+      jobs[j].profile[idx] = (float)X[(size_t)j * D + i];           // vdef is a float (profile.h:70-72, libsac.cpp:394)
+    }
+  }
+  std::vector<int> cj, cc;
+  size_t stride;
+  int rc = e->run_predict(jobs, cj, cc, stride);
+  if (rc) return rc;
+  return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
+}
+
+int sac_eval_population(sac_engine *h, const sac_window *w, int from, int n, const float *base_profile, const int *dims, int D,
+                        const double *X, int P, int cost_kind, int optk, double *cost)
+{
+  if (P <= 0 || !base_profile) { set_error("sac_eval_population: bad argument"); return SAC_E_ARG; }
+  std::vector<const sac_window *> wins(P, w);
+  std::vector<int> fr(P, from), nn(P, n);
+  std::vector<float> bases((size_t)P * kProfileSize);
+  for (int p = 0; p < P; p++) std::memcpy(&bases[(size_t)p * kProfileSize], base_profile, sizeof(float) * kProfileSize);
+  return sac_eval_jobs(h, P, wins.data(), fr.data(), nn.data(), bases.data(), dims, D, X, cost_kind, optk, cost);
+}
+
+int sac_cost(sac_engine *h, int cost_kind, const int32_t *bufs, int count, int n, double *cost)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !bufs || count <= 0 || n <= 0 || !cost) { set_error("sac_cost: bad argument"); return SAC_E_ARG; }
+  e->begin_call();
+  SACB_CUDA(cudaSetDevice(e->device));
+  // one mono pseudo-window so that run_cost's bookkeeping applies; residuals are uploaded in place of predictor output
+  Window w; w.eng = e; w.nch = 1; w.numsamples = n; w.d_planes[0] = w.d_planes[1] = nullptr;
+  int32_t mn = 0, mx = 0;
+  for (size_t i = 0; i < (size_t)count * n; i++) { mn = std::min(mn, bufs[i]); mx = std::max(mx, bufs[i]); }
+  const int32_t R = std::max(-(long long)mn, (long long)mx) > 0 ? (int32_t)std::max(-(long long)mn, (long long)mx) : 1;
+  w.minmax[0] = 0; w.minmax[1] = R; w.minmax[2] = 0; w.minmax[3] = R;
+  std::vector<Job> jobs(count);
+  std::vector<int> cj(count), cc(count, 0);
+  for (int c = 0; c < count; c++) { jobs[c].win = &w; jobs[c].from = 0; jobs[c].n = n; jobs[c].k = 1; cj[c] = c; }
+  const size_t stride = ((size_t)n + 31) & ~size_t(31);
+  SACB_CUDA(e->d_resid.reserve(stride * count));
+  SACB_CUDA(e->d_sums.reserve((size_t)3 * count));
+  SACB_CUDA(e->d_flags.reserve((size_t)4 * count));
+  SACB_CUDA(cudaMemsetAsync(e->d_flags.p, 0, sizeof(int) * 4 * count, e->stream));
+  std::vector<long long> sums(3 * (size_t)count, 0);
+  for (int c = 0; c < count; c++) {
+    const int32_t *b = bufs + (size_t)c * n;
+    long long l1 = 0, sq = 0;
+    for (int i = 0; i < n; i++) { l1 += std::llabs((long long)b[i]); sq += (long long)b[i] * b[i]; }
+    sums[c] = l1; sums[count + c] = sq;
+    SACB_CUDA(cudaMemcpyAsync(e->d_resid.p + (size_t)c * stride, b, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  }
+  SACB_CUDA(cudaMemcpyAsync(e->d_sums.p, sums.data(), sizeof(long long) * 3 * count, cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
+}
+
+} // extern "C"

@@ -1,0 +1,127 @@
+// engine.h -- the per-GPU engine behind the C ABI: HBM pools, model tables, batched launches.
+#ifndef SAC_B200_ENGINE_H
+#define SAC_B200_ENGINE_H
+#include "bitplane.h"
+#include "chain.h"
+#include "sac_b200.h"
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+namespace sacb {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define SACB_CUDA(call)                                              \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return ::sacb::cuda_fail(e__, #call);    \
+  } while (0)
+
+// grow-only device buffer
+template <class T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) { want = n; e = cudaMalloc(&p, want * sizeof(T)); }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, (n + n / 8) * sizeof(T));
+    if (e == cudaSuccess) cap = n + n / 8;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Window {           // sac_window
+  struct Engine *eng;
+  int nch, numsamples;
+  int32_t minmax[4];
+  int32_t *d_planes[2];   // HBM, mean-free
+};
+
+// one evaluation job: a profile on a window range
+struct Job {
+  const Window *win;
+  int from, n, k;
+  float profile[kProfileSize];
+};
+
+struct Engine {           // sac_engine
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  BitplaneTables bt;
+  int smem_bytes = 72 * 1024;
+  long long launches = 0;
+  double last_ms[3] = {0, 0, 0};
+  long long last_launches[3] = {0, 0, 0};
+
+  DevBuf<ChainDesc> d_descs;
+  PinBuf<ChainDesc> h_descs;
+  DevBuf<double> d_scratch;
+  DevBuf<int32_t> d_resid;
+  DevBuf<long long> d_sums;       // per chain: l1, sq, nbytes
+  DevBuf<int> d_flags;            // per chain: flags, maxbpn
+  PinBuf<long long> h_sums;
+  PinBuf<int> h_flags;
+  DevBuf<BpJob> d_bpjobs;
+  PinBuf<BpJob> h_bpjobs;
+  DevBuf<uint32_t> d_csig0;
+  DevBuf<unsigned int> d_hist;
+  DevBuf<double> d_cost;
+  PinBuf<double> h_cost;
+  DevBuf<uint8_t> d_bytes;        // payload / msb scratch
+  PinBuf<int32_t> h_stage;        // pinned staging for sample uploads
+
+  int init(int dev);
+  void destroy();
+  // residuals of every chain of `jobs` into d_resid (layout: chain c at c*stride); returns 0
+  int run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride);
+  // per-job cost (sum over channels) for residuals left by run_predict
+  int run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vector<int> &chain_job, const std::vector<int> &chain_ch,
+               size_t stride, double *cost);
+  void begin_call();
+};
+
+// kernels (predictor.cu, cost.cu)
+cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
+cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
+                           size_t hist_stride, double *out, cudaStream_t stream);
+cudaError_t launch_golomb(const int32_t *resid, size_t stride, const int *ns, int nchains, double *out, cudaStream_t stream);
+
+// host-side parameter mapping (FrameCoder::SetParam, libsac.cpp:37-92)
+struct HostParam {
+  int nA, nB, nM0, nS0, nS1, ch_ref, lm_n, bias_scale;
+  int vn[2][4];
+  double vmu[2][4], vmudecay[2][4], vpowdecay[2][4];
+  double lambda[2], ols_nu[2], mu_mix[2], mu_mix_beta[2], beta_sum[2], beta_pow[2], beta_add[2];
+  double bias_mu[2], lm_alpha, proj_alpha[2];
+};
+HostParam map_profile(const float *profile);
+long long chain_scratch_doubles(const HostParam &hp, int coded_ch, int nch);
+// fills the encoder descriptor of coded channel `cc` (0/1); returns the actual channel index it codes
+int fill_chain(ChainDesc &d, const HostParam &hp, int nch, int cc, int k, const int32_t *const *planes, int from, int n,
+               const int32_t *minmax);
+
+extern const float kBaseProfile[kProfileSize][3];
+
+} // namespace sacb
+#endif

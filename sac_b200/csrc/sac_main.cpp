@@ -1,0 +1,199 @@
+// sac_main.cpp -- the `sac` command line of the reference (/root/reference src/main.cpp, src/cmdline.cpp), same flags,
+// driving libsac_b200 through its C ABI. Options the B200 path adds: --gpu=N, --frame-parallel.
+#include "sac_b200.h"
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+static const char kHelp[] =
+    "usage: sac [--options] input output\n\n"
+    "  --encode            encode input.wav to output.sac (def)\n"
+    "    --normal|high|veryhigh|extrahigh compression (def=normal)\n"
+    "    --best            you asked for it\n\n"
+    "  --decode            decode input.sac to output.wav\n"
+    "  --list              list info about input.sac\n"
+    "  --listfull          verbose info about input\n"
+    "  --verbose           verbose output\n\n"
+    "  supported types: 1-16 bit, mono/stereo pcm\n"
+    "  advanced options    (automatically set)\n"
+    "   --optimize=#       frame-based optimization\n"
+    "     no|s,n,c,k       s=[0,1.0],n=[0,10000]\n"
+    "                      c=[l1,rms,glb,ent,bpn] k=[1,32]\n"
+    "   --opt-cfg=#        configure optimization method\n"
+    "     dds,nt,s         nt=generation size (GPU batch),s=search radius (def=0.2)\n"
+    "   --opt-reset        reset opt params at frame boundaries\n"
+    "   --mt-mode=n        accepted, ignored (parallelism is the GPU's)\n"
+    "   --zero-mean        zero-mean input\n"
+    "   --adapt-block      accepted (adaptive splitting not implemented)\n"
+    "   --framelen=n       def=20 seconds\n"
+    "   --sparse-pcm       accepted (pcm modelling not implemented)\n"
+    "  B200 options\n"
+    "   --gpu=n            CUDA device (def=0)\n"
+    "   --frame-parallel   search all frames of the file concurrently (implies --opt-reset semantics)\n";
+
+static std::string upper(std::string s) { for (auto &c : s) c = (char)std::toupper((unsigned char)c); return s; }
+static std::vector<std::string> split(const std::string &s, char d)
+{
+  std::vector<std::string> out; std::string cur;
+  for (char c : s) { if (c == d) { if (!cur.empty()) out.push_back(cur); cur.clear(); } else cur += c; }
+  if (!cur.empty()) out.push_back(cur);
+  return out;
+}
+static uint32_t rd32(const uint8_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24); }
+static uint16_t rd16(const uint8_t *b) { return (uint16_t)(b[0] | (b[1] << 8)); }
+static std::string time_str(long long numsamples, long long sr)
+{
+  int h = 0, m = 0, s = 0, ms = 0;
+  if (numsamples > 0 && sr > 0) {
+    while (numsamples >= 3600 * sr) { ++h; numsamples -= 3600 * sr; }
+    while (numsamples >= 60 * sr) { ++m; numsamples -= 60 * sr; }
+    while (numsamples >= sr) { ++s; numsamples -= sr; }
+    ms = (int)std::round((numsamples * 1000.) / sr);
+  }
+  char b[64]; std::snprintf(b, sizeof b, "%02d:%02d:%02d.%d", h, m, s, ms);
+  return b;
+}
+static void print_md5(const uint8_t d[16]) { for (int i = 0; i < 16; i++) std::printf("%x", (int)d[i]); }   // cmdline.cpp:313 (no zero padding)
+
+static int list_file(const std::string &path, bool full)
+{
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { std::cout << "could not open\n"; return 1; }
+  std::vector<uint8_t> b((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::cout << "ok (" << b.size() << " Bytes)\n";
+  if (b.size() < 38 || std::memcmp(b.data(), "SAC2", 4)) { std::cout << "warning: input is not a valid .sac file\n"; return 1; }
+  const int nch = rd16(&b[4]), sr = (int)rd32(&b[6]), bits = rd16(&b[10]);
+  const uint32_t ns = rd32(&b[12]);
+  const int fl = b[16];
+  const uint32_t md = rd32(&b[18]);
+  const double bps = (b.size() * 8.0) / ((double)ns * nch);
+  std::printf("  WAVE  Codec: PCM (%d kbps)\n  %dHz %d Bit  %s\n  %u Samples [%s]\n", (int)std::round((sr * nch * bps) / 1000), sr, bits,
+              nch == 1 ? "Mono" : "Stereo", ns, time_str(ns, sr).c_str());
+  std::printf("  Profile: %ds\n  Ratio:   %.3f bps\n\n  Audio MD5: ", fl, bps);
+  size_t pos = 22 + md;
+  print_md5(&b[pos]);
+  std::printf("\n");
+  pos += 16;
+  if (full) {                                                         // Codec::ScanFrames (libsac.cpp:659-693)
+    int frame = 1, coef = 0, blk = 0;
+    while (pos + 4 <= b.size()) {
+      std::printf("Frame %d: %u samples \n", frame, rd32(&b[pos]));
+      pos += 4 + 58 * 4; coef += 58 * 4;
+      for (int ch = 0; ch < nch && pos + 18 <= b.size(); ch++) {
+        const uint32_t bs = rd32(&b[pos]);
+        const uint16_t flag = rd16(&b[pos + 16]);
+        std::printf("  Channel %d: %u bytes\n    Bpn: %d, sparse_pcm: %d\n    mean: %d, min: %d, max: %d\n", ch, bs, flag & 0xff, flag >> 9,
+                    (int32_t)rd32(&b[pos + 4]), (int32_t)rd32(&b[pos + 8]), (int32_t)rd32(&b[pos + 12]));
+        pos += 18 + bs; blk += 18;
+      }
+      frame++;
+    }
+    std::printf("Frames   %d\nHdr_size %d (coefs %d,block %d)\n", frame - 1, coef + blk, coef, blk);
+  }
+  return 0;
+}
+
+int main(int argc, const char *argv[])
+{
+  std::cout << "Sac-B200 v0.1 - Lossless Audio Coder, B200-native encode path (model of Sac v0.7.25 by Sebastian Lehmann)\n\n";
+  if (argc < 2) { std::cout << kHelp; return 1; }
+  enum { ENCODE, DECODE, LIST, LISTFULL } mode = ENCODE;
+  sac_cfg cfg;
+  sac_cfg_default(&cfg);
+  std::string in, out;
+  bool first = true;
+  int gpu = 0;
+  for (int k = 1; k < argc; k++) {
+    const std::string param = argv[k];
+    const std::string up = upper(param);
+    std::string key = up, val;
+    const size_t eq = up.find('=');
+    if (eq != std::string::npos) { key = up.substr(0, eq); val = up.substr(eq + 1); }
+    if (param.size() > 1 && param[0] == '-' && param[1] == '-') {
+      if (key == "--ENCODE") mode = ENCODE;
+      else if (key == "--DECODE") mode = DECODE;
+      else if (key == "--LIST") mode = LIST;
+      else if (key == "--LISTFULL") mode = LISTFULL;
+      else if (key == "--VERBOSE") cfg.verbose = val.size() ? std::max(0, std::atoi(val.c_str())) : 1;
+      else if (key == "--NORMAL" || key == "--HIGH" || key == "--VERYHIGH" || key == "--EXTRAHIGH" || key == "--BEST" || key == "--INSANE")
+        sac_cfg_preset(&cfg, key.c_str() + 2);
+      else if (key == "--OPTIMIZE") {
+        if (val == "NO" || val == "0") cfg.optimize = 0;
+        else {
+          auto vs = split(val, ',');
+          if (vs.size() >= 2) {
+            cfg.fraction = std::clamp(std::atof(vs[0].c_str()), 0., 1.);
+            cfg.maxnfunc = std::clamp(std::atoi(vs[1].c_str()), 0, 50000);
+            if (vs.size() >= 3) {
+              if (vs[2] == "L1") cfg.cost_kind = SAC_COST_L1;
+              else if (vs[2] == "RMS") cfg.cost_kind = SAC_COST_RMS;
+              else if (vs[2] == "GLB") cfg.cost_kind = SAC_COST_GOLOMB;
+              else if (vs[2] == "ENT") cfg.cost_kind = SAC_COST_ENTROPY;
+              else if (vs[2] == "BPN") cfg.cost_kind = SAC_COST_BITPLANE;
+              else std::cerr << "warning: unknown cost function '" << vs[2] << "'\n";
+            }
+            if (vs.size() >= 4) cfg.optk = std::clamp(std::atoi(vs[3].c_str()), 1, 32);
+            cfg.optimize = (cfg.fraction > 0. && cfg.maxnfunc > 0) ? 1 : 0;
+          } else std::cerr << "unknown option: " << val << '\n';
+        }
+      } else if (key == "--FRAMELEN") { if (val.size()) cfg.max_framelen = std::max(0, std::atoi(val.c_str())); }
+      else if (key == "--MT-MODE") {}
+      else if (key == "--SPARSE-PCM") cfg.sparse_pcm = !(val == "NO" || val == "0");
+      else if (key == "--STEREO-MS") {}
+      else if (key == "--OPT-RESET") cfg.reset = 1;
+      else if (key == "--OPT-CFG") {
+        auto vs = split(val, ',');
+        if (vs.size() >= 1 && vs[0] != "DDS") std::cerr << "  warning: only opt='DDS' is implemented\n";
+        if (vs.size() >= 2) cfg.num_threads = std::clamp(std::atoi(vs[1].c_str()), 0, 4096);
+        if (vs.size() >= 3) cfg.sigma = std::clamp(std::atof(vs[2].c_str()), 0., 1.);
+      } else if (key == "--ADAPT-BLOCK") cfg.adapt_block = !(val == "NO" || val == "0");
+      else if (key == "--ZERO-MEAN") cfg.zero_mean = !(val == "NO" || val == "0");
+      else if (key == "--GPU") gpu = std::atoi(val.c_str());
+      else if (key == "--FRAME-PARALLEL") cfg.frame_parallel = 1;
+      else std::cerr << "warning: unknown option '" << param << "'\n";
+    } else {
+      if (first) { in = param; first = false; } else out = param;
+    }
+  }
+  if (mode == LIST || mode == LISTFULL) {
+    std::cout << "Open: '" << in << "': ";
+    return list_file(in, mode == LISTFULL);
+  }
+  sac_engine *eng = sac_engine_create(gpu);
+  if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
+  sac_file_stats st;
+  int rc;
+  if (mode == ENCODE) {
+    std::cout << "Open: '" << in << "'\nCreate: '" << out << "'\n";
+    std::printf("  Profile: %ds%s%s\n", cfg.max_framelen, cfg.zero_mean ? " zero-mean" : "", cfg.frame_parallel ? " frame-parallel" : "");
+    if (cfg.optimize) {
+      const char *cs[] = {"L1", "rms", "ent", "glb", "bpn"};
+      std::printf("  Optimize: DDS %.1f%%,n=%d,%s,k=%d,gen=%d\n", cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk, cfg.num_threads);
+    }
+    rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
+    if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
+    std::printf("  %dHz %d Bit  %s  %d Samples [%s]\n", st.samplerate, st.bits, st.nch == 1 ? "Mono" : "Stereo", st.numsamples,
+                time_str(st.numsamples, st.samplerate).c_str());
+    std::printf("  MD5:     "); print_md5(st.md5); std::printf("\n");
+    const double r = st.out_bytes * 100.0 / st.in_bytes, bps = (st.out_bytes * 8.) / ((double)st.numsamples * st.nch);
+    const double xr = st.seconds > 0 ? (st.numsamples / (double)st.samplerate) / st.seconds : 0.0;
+    std::printf("\n  %lld->%lld=%.1f%% (%.3f bps)  %.3fx\n", st.in_bytes, st.out_bytes, r, bps, xr);
+  } else {
+    std::cout << "Open: '" << in << "'\nCreate: '" << out << "'\n";
+    rc = sac_decode_file(eng, in.c_str(), out.c_str(), &st);
+    if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
+    const double xr = st.seconds > 0 ? (st.numsamples / (double)st.samplerate) / st.seconds : 0.0;
+    std::printf("\n  Speed %.3fx\n  Audio MD5: ", xr);
+    if (st.md5_ok) std::printf("ok\n"); else { std::printf("Error ("); print_md5(st.md5); std::printf(")\n"); }
+  }
+  std::printf("\n  Time:    [%02d:%02d:%02d]\n", (int)(st.seconds / 3600), (int)(st.seconds / 60) % 60, (int)st.seconds % 60);
+  sac_engine_destroy(eng);
+  return rc ? 1 : 0;
+}
