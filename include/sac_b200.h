@@ -49,8 +49,14 @@ long long sac_engine_launches(const sac_engine *);
  * [0] predictor [1] bitplane [2] entropy/other; out_ms[3], out_launches[3] */
 void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_launches);
 
+/* measured DFMA throughput of the device (GFLOP/s, 2 flop per fma; CUDA events): the fp64 roofline denominator */
+double sac_fp64_peak_gflops(sac_engine *);
+
 /* ---- profile (SacProfile::LoadBaseProfile, src/libsac/profile.cpp:3-89) ------------------------------------------ */
 int sac_base_profile(float *vmin, float *vmax, float *vdef); /* 58 each; returns 58 */
+
+/* LogDomain stretch[32768] / squash[4095] tables of the bitplane model (src/model/domain.h:7-61), canonical math, host only */
+void sac_model_tables(int16_t *stretch, int16_t *squash);
 
 /* ---- windows ---------------------------------------------------------------------------------------------------- */
 /* planes[ch][numsamples] must already be mean-free (FrameCoder::Predict, libsac.cpp:452-458);
@@ -66,6 +72,12 @@ int sac_predict(sac_engine *, const sac_window *, const float *profiles, int P, 
 
 /* ---- CostFunction::Calc (src/libsac/cost.h) on host residual arrays: bufs[count][n] -> cost[count] ---------------- */
 int sac_cost(sac_engine *, int cost_kind, const int32_t *bufs, int count, int n, double *cost);
+
+/* ---- BitplaneCoder::Encode / Decode over RangeCoderSH (src/libsac/vle.h:51-53, src/model/range.h:45-60) -----------
+ * resid[n]: signed residuals (S2U-mapped inside, as FrameCoder::CnvError_S2U). maxbpn_io: in <0 = derive from the
+ * data (iLog2 of the largest mapped value), out = the value used. Payload to out (cap bytes), length to *out_len. */
+int sac_bitplane_encode(sac_engine *, const int32_t *resid, int n, int *maxbpn_io, uint8_t *out, long long cap, long long *out_len);
+int sac_bitplane_decode(sac_engine *, const uint8_t *payload, long long len, int n, int maxbpn, int32_t *resid_out);
 
 /* ---- population evaluation -------------------------------------------------------------------------------------
  * cost[p] = sum over channels of Cost(PredictFrame(profile with dims[i] <- (float)X[p][i], window, k=optk)).
@@ -110,6 +122,11 @@ int sac_cfg_preset(sac_cfg *, const char *name);
 int sac_frames_encode(sac_engine *, const sac_cfg *, int nch, int max_framesize, int nframes,
                       const int32_t *const *planes, const int *numsamples, float *profile_io, uint8_t *out, long long cap,
                       long long *out_len);
+/* the same with the frames already resident in HBM (sac_window_create on mean-free planes; means[f*nch+ch] go into
+ * the block headers): the timed region of bench.py's device-resident throughput */
+int sac_frames_encode_resident(sac_engine *, const sac_cfg *, int nch, int max_framesize, int nframes,
+                               const sac_window *const *wins, const int32_t *means, float *profile_io, uint8_t *out,
+                               long long cap, long long *out_len);
 /* one frame record -> samples (mean restored). Returns bytes consumed (>0) or <0. planes_out[ch][cap_samples]. */
 long long sac_frame_decode(sac_engine *, int nch, const uint8_t *in, long long len, int32_t *const *planes_out,
                            int cap_samples, int *numsamples);

@@ -73,6 +73,8 @@ def lib():
         L.sac_window_destroy.argtypes = [C.c_void_p]
         L.sac_predict.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _intp]
         L.sac_cost.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_int, C.c_int, _f64p]
+        L.sac_bitplane_encode.argtypes = [C.c_void_p, _i32p, C.c_int, _intp, _u8p, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sac_bitplane_decode.argtypes = [C.c_void_p, _u8p, C.c_longlong, C.c_int, C.c_int, _i32p]
         L.sac_eval_population.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _f32p, _intp, C.c_int, _f64p, C.c_int,
                                           C.c_int, C.c_int, _f64p]
         L.sac_eval_jobs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _intp, _intp, _f32p, _intp, C.c_int, _f64p,
@@ -83,6 +85,10 @@ def lib():
         L.sac_cfg_preset.argtypes = [C.POINTER(Cfg), C.c_char_p]
         L.sac_frames_encode.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_int, C.c_int, C.c_int, C.POINTER(_i32p), _intp, _f32p,
                                         _u8p, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sac_frames_encode_resident.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), _i32p,
+                                                 _f32p, _u8p, C.c_longlong, C.POINTER(C.c_longlong)]
+        L.sac_fp64_peak_gflops.restype = C.c_double
+        L.sac_fp64_peak_gflops.argtypes = [C.c_void_p]
         L.sac_frame_decode.restype = C.c_longlong
         L.sac_frame_decode.argtypes = [C.c_void_p, C.c_int, _u8p, C.c_longlong, C.POINTER(_i32p), C.c_int, _intp]
         L.sac_encode_file.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
@@ -209,6 +215,23 @@ class Engine:
         _chk(lib().sac_cost(self.h, kind, _p(bufs, _i32p), bufs.shape[0], bufs.shape[1], _p(out, _f64p)), "sac_cost")
         return out
 
+    def bitplane_encode(self, resid, maxbpn=-1):
+        """BitplaneCoder::Encode over RangeCoderSH: signed residuals -> (payload bytes, maxbpn)"""
+        resid = np.ascontiguousarray(resid, np.int32)
+        cap = 4 * len(resid) + 1024
+        out = np.zeros(cap, np.uint8)
+        olen = C.c_longlong(0)
+        mb = C.c_int(maxbpn)
+        _chk(lib().sac_bitplane_encode(self.h, _p(resid, _i32p), len(resid), C.byref(mb), _p(out, _u8p), cap, C.byref(olen)),
+             "sac_bitplane_encode")
+        return out[:olen.value].copy(), mb.value
+
+    def bitplane_decode(self, payload, n, maxbpn):
+        payload = np.ascontiguousarray(payload, np.uint8)
+        out = np.zeros(n, np.int32)
+        _chk(lib().sac_bitplane_decode(self.h, _p(payload, _u8p), len(payload), n, maxbpn, _p(out, _i32p)), "sac_bitplane_decode")
+        return out
+
     def eval_population(self, win, frm, n, base, X, cost_kind, optk=4, dims=None):
         """Opt::eval_points_mt over the cost lambda of FrameCoder::Optimize: X[P,D] -> cost[P]"""
         X = np.ascontiguousarray(np.atleast_2d(X), np.float64)
@@ -233,6 +256,22 @@ class Engine:
         _chk(lib().sac_frames_encode(self.h, C.byref(cfg), nch, max_framesize, len(keep), arr, _p(ns, _intp), _p(prof, _f32p),
                                      _p(out, _u8p), cap, C.byref(olen)), "sac_frames_encode")
         return out[:olen.value].copy(), prof
+
+    def frames_encode_resident(self, cfg, windows, means, max_framesize, profile=None):
+        """frames already in HBM (Window objects of mean-free planes); means: per frame per channel"""
+        nch = windows[0].nch
+        arr = (C.c_void_p * len(windows))(*[w.h for w in windows])
+        mm = np.ascontiguousarray(means, np.int32).reshape(-1)
+        prof = np.ascontiguousarray(base_profile()[2] if profile is None else profile, np.float32).copy()
+        cap = int(sum(w.n for w in windows) * nch * 5 + 4096 * len(windows))
+        out = np.zeros(cap, np.uint8)
+        olen = C.c_longlong(0)
+        _chk(lib().sac_frames_encode_resident(self.h, C.byref(cfg), nch, max_framesize, len(windows), arr, _p(mm, _i32p), _p(prof, _f32p),
+                                              _p(out, _u8p), cap, C.byref(olen)), "sac_frames_encode_resident")
+        return out[:olen.value].copy(), prof
+
+    def fp64_peak_gflops(self):
+        return float(lib().sac_fp64_peak_gflops(self.h))
 
     def frame_decode(self, nch, data, cap_samples):
         data = np.ascontiguousarray(data, np.uint8)

@@ -521,16 +521,22 @@ __global__ void laplace_table_kernel(uint16_t *tab, int lap_bits)
 size_t bitplane_state_bytes() { return sizeof(BpState); }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-cudaError_t BitplaneTables::init(cudaStream_t stream)
+// LogDomain (domain.h:17-31) in canonical math; equality with the reference's libm tables is asserted in tests
+void compute_logdomain_tables(int16_t *st, int16_t *sq)
 {
   using namespace sac_canon;
-  std::vector<int16_t> st(PSCALE), sq(4095);
-  // LogDomain (domain.h:17-31) in canonical math; equality with the libm tables is asserted in tests
   for (int i = 0; i < PSCALE; i++) {
     const double f = (i > 1 ? i : 1) / (double)PSCALE;
     st[i] = (int16_t)c_round(c_log(f / (1.0 - f)) * 256);
   }
   for (int i = -2047; i <= 2047; i++) sq[i + 2047] = (int16_t)c_round(PSCALE / (1.0 + c_exp(-double(i) / 256.0)));
+}
+
+cudaError_t BitplaneTables::init(cudaStream_t stream)
+{
+  using namespace sac_canon;
+  std::vector<int16_t> st(PSCALE), sq(4095);
+  compute_logdomain_tables(st.data(), sq.data());
   uint16_t dv[304], pl[32], si[16];
   for (int i = 0; i < 304; i++) dv[i] = (uint16_t)(PSCALE / (i + 3));
   for (int i = 0; i < 32; i++) {

@@ -284,13 +284,22 @@ void analyse_channel(std::vector<int32_t> &s, int zero_mean, int32_t &mean, int3
 } // namespace
 
 static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
-                         const int *numsamples, float *profile_io, std::vector<uint8_t> &out)
+                         const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
+                         const sac_window *const *resident = nullptr, const int32_t *resident_means = nullptr)
 {
   std::vector<FrameWork> fw(nframes);
-  struct Cleanup { std::vector<FrameWork> &f; ~Cleanup() { for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw};
-  // ---- analysis + upload ----
+  struct Cleanup { std::vector<FrameWork> &f; bool own; ~Cleanup() { if (own) for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw, resident == nullptr};
+  // ---- analysis + upload (or windows already resident in HBM) ----
   for (int f = 0; f < nframes; f++) {
     FrameWork &w = fw[f];
+    if (resident) {
+      w.win = const_cast<Window *>(reinterpret_cast<const Window *>(resident[f]));
+      if (!w.win || w.win->nch != nch) { set_error("resident window mismatch"); return SAC_E_ARG; }
+      w.n = w.win->numsamples;
+      for (int ch = 0; ch < nch; ch++) { w.mean[ch] = resident_means ? resident_means[f * nch + ch] : 0; w.mm[2 * ch] = w.win->minmax[2 * ch]; w.mm[2 * ch + 1] = w.win->minmax[2 * ch + 1]; }
+      if (w.n <= 0 || w.n > max_framesize) { set_error("frame length out of range"); return SAC_E_ARG; }
+      continue;
+    }
     w.n = numsamples[f];
     if (w.n <= 0 || w.n > max_framesize) { set_error("frame length out of range"); return SAC_E_ARG; }
     std::vector<std::vector<int32_t>> s(nch);
@@ -686,6 +695,69 @@ double sac_dds_run(int D, const double *xmin, const double *xmax, const double *
   return s.best_cost();
 }
 
+int sac_bitplane_encode(sac_engine *h, const int32_t *resid, int n, int *maxbpn_io, uint8_t *out, long long cap, long long *out_len)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !resid || n <= 0 || !out_len) { set_error("sac_bitplane_encode: bad argument"); return SAC_E_ARG; }
+  SACB_CUDA(cudaSetDevice(e->device));
+  e->begin_call();
+  const size_t stride = ((size_t)n + 31) & ~size_t(31), bcap = (size_t)n * 4 + 1024;
+  SACB_CUDA(e->d_resid.reserve(stride));
+  SACB_CUDA(e->d_csig0.reserve(65536));
+  SACB_CUDA(e->d_bytes.reserve(bcap));
+  SACB_CUDA(e->d_sums.reserve(4));
+  SACB_CUDA(e->d_flags.reserve(4));
+  SACB_CUDA(e->h_bpjobs.reserve(1));
+  SACB_CUDA(e->d_bpjobs.reserve(1));
+  SACB_CUDA(cudaMemcpyAsync(e->d_resid.p, resid, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+  BpJob &b = e->h_bpjobs.p[0];
+  std::memset(&b, 0, sizeof(b));
+  b.buf = e->d_resid.p; b.n = n; b.signed_input = 1; b.maxbpn = maxbpn_io ? *maxbpn_io : -1;
+  b.csig0 = e->d_csig0.p; b.out = e->d_bytes.p; b.nbytes = e->d_sums.p; b.maxbpn_out = e->d_flags.p;
+  SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob), cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+  SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, 1, 1, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+  e->launches++; e->last_launches[1]++;
+  long long nb = 0; int mb = 0;
+  SACB_CUDA(cudaMemcpyAsync(&nb, e->d_sums.p, sizeof(nb), cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaMemcpyAsync(&mb, e->d_flags.p, sizeof(mb), cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->last_ms[1] += ms; }
+  *out_len = nb;
+  if (maxbpn_io) *maxbpn_io = mb;
+  if (!out || nb > cap) { set_error("output buffer too small"); return SAC_E_ARG; }
+  SACB_CUDA(cudaMemcpy(out, e->d_bytes.p, (size_t)nb, cudaMemcpyDeviceToHost));
+  return SAC_OK;
+}
+
+int sac_bitplane_decode(sac_engine *h, const uint8_t *payload, long long len, int n, int maxbpn, int32_t *resid_out)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !payload || len < 0 || n <= 0 || maxbpn < 0 || maxbpn > 30 || !resid_out) { set_error("sac_bitplane_decode: bad argument"); return SAC_E_ARG; }
+  SACB_CUDA(cudaSetDevice(e->device));
+  e->begin_call();
+  const size_t stride = ((size_t)n + 31) & ~size_t(31), pl = ((size_t)len + 15) & ~size_t(15);
+  SACB_CUDA(e->d_resid.reserve(stride));
+  SACB_CUDA(e->d_csig0.reserve(65536));
+  SACB_CUDA(e->d_bytes.reserve(pl + stride + 16));
+  SACB_CUDA(e->h_bpjobs.reserve(1));
+  SACB_CUDA(e->d_bpjobs.reserve(1));
+  if (len) SACB_CUDA(cudaMemcpyAsync(e->d_bytes.p, payload, (size_t)len, cudaMemcpyHostToDevice, e->stream));
+  BpJob &b = e->h_bpjobs.p[0];
+  std::memset(&b, 0, sizeof(b));
+  b.buf = e->d_resid.p; b.n = n; b.maxbpn = maxbpn; b.csig0 = e->d_csig0.p; b.in = e->d_bytes.p; b.in_len = len; b.msb = e->d_bytes.p + pl;
+  SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob), cudaMemcpyHostToDevice, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
+  SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, 1, 2, e->stream));
+  SACB_CUDA(cudaEventRecord(e->ev[3], e->stream));
+  e->launches++; e->last_launches[1]++;
+  SACB_CUDA(cudaMemcpyAsync(resid_out, e->d_resid.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaStreamSynchronize(e->stream));
+  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->last_ms[1] += ms; }
+  return SAC_OK;
+}
+
 void sac_cfg_default(sac_cfg *c)
 {
   std::memset(c, 0, sizeof(*c));
@@ -714,6 +786,20 @@ int sac_frames_encode(sac_engine *h, const sac_cfg *cfg, int nch, int max_frames
   if (!e || !cfg || nch < 1 || nch > 2 || nframes <= 0 || !planes || !numsamples || !profile_io || !out_len) { set_error("sac_frames_encode: bad argument"); return SAC_E_ARG; }
   std::vector<uint8_t> buf;
   int rc = frames_encode(e, *cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, buf);
+  if (rc) return rc;
+  *out_len = (long long)buf.size();
+  if ((long long)buf.size() > cap || !out) { set_error("output buffer too small"); return SAC_E_ARG; }
+  std::memcpy(out, buf.data(), buf.size());
+  return SAC_OK;
+}
+
+int sac_frames_encode_resident(sac_engine *h, const sac_cfg *cfg, int nch, int max_framesize, int nframes, const sac_window *const *wins,
+                               const int32_t *means, float *profile_io, uint8_t *out, long long cap, long long *out_len)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e || !cfg || nch < 1 || nch > 2 || nframes <= 0 || !wins || !profile_io || !out_len) { set_error("sac_frames_encode_resident: bad argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> buf;
+  int rc = frames_encode(e, *cfg, nch, max_framesize, nframes, nullptr, nullptr, profile_io, buf, wins, means);
   if (rc) return rc;
   *out_len = (long long)buf.size();
   if ((long long)buf.size() > cap || !out) { set_error("output buffer too small"); return SAC_E_ARG; }

@@ -64,7 +64,25 @@ __global__ void golomb_kernel(const int32_t *__restrict__ resid, size_t stride, 
   out[c] = n ? (double)nbits / 8. : 0.0;
 }
 
+// 8 independent DFMA chains per thread: the fp64 pipe's issue-bound peak
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed)
+{
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 } // namespace
+
+cudaError_t launch_dfma_peak(double *out, int blocks, int iters, cudaStream_t stream)
+{
+  dfma_peak_kernel<<<blocks, 256, 0, stream>>>(out, iters, 1.0);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream)

@@ -304,6 +304,30 @@ void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_
   for (int i = 0; i < 3; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
 }
 
+double sac_fp64_peak_gflops(sac_engine *h)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e) return -1.0;
+  cudaSetDevice(e->device);
+  const int blocks = 148 * 8, iters = 1 << 15;
+  if (e->d_cost.reserve((size_t)blocks * 256) != cudaSuccess) return -1.0;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e->ev[2], e->stream);
+    if (launch_dfma_peak(e->d_cost.p, blocks, iters, e->stream) != cudaSuccess) return -1.0;
+    cudaEventRecord(e->ev[3], e->stream);
+    cudaStreamSynchronize(e->stream);
+    e->launches++;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]);
+    const double gf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e9;
+    if (rep > 0 && gf > best) best = gf;
+  }
+  return best;
+}
+
+void sac_model_tables(int16_t *stretch, int16_t *squash) { compute_logdomain_tables(stretch, squash); }
+
 int sac_base_profile(float *vmin, float *vmax, float *vdef)
 {
   for (int i = 0; i < kProfileSize; i++) {

@@ -105,6 +105,7 @@ struct Engine {           // sac_engine
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream);
+cudaError_t launch_dfma_peak(double *out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_golomb(const int32_t *resid, size_t stride, const int *ns, int nchains, double *out, cudaStream_t stream);
 
 // host-side parameter mapping (FrameCoder::SetParam, libsac.cpp:37-92)

@@ -12,7 +12,7 @@
 // so the scalar warp's updates overlap the tap warps' C(t)+A(t+1).
 //
 // Arithmetic is the canonical order of DESIGN.md (fma placement and reduction trees spelled out; compiled with
-// --fmad=false): tests compare residuals bit-for-bit with oracle/sac_oracle.cpp in SACO_ORDER_B200/SACO_MATH_CANON.
+// --fmad=false): the -m gpu tests compare residuals bit-for-bit with the CPU restatement kept under oracle/.
 // Reference behaviour restated here: /root/reference src/libsac/pred.cpp:4-45, src/pred/{ols.cpp,ls.h,cascade.h,
 // blend.h,rls.cpp,rls.h,bias.h}, src/common/math.h:14-78, src/libsac/libsac.cpp:94-199.
 #include "chain.h"

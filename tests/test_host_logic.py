@@ -1,0 +1,91 @@
+"""CPU-only checks of the product's host side: the C ABI loads and exports every declared symbol, the DDS driver
+reproduces the reference's candidate sequence, presets, model tables. No compute entry point is called."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sac_b200 as sb
+from helpers import sha
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sac_b200.h")).read()
+    names = set(re.findall(r"\b(sac_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"sac_eval_fn"}
+    assert len(names) >= 20
+    L = sb.lib()
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sac_b200" in L.sac_version()
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sb.SacError):
+        sb.Engine(0)
+    assert b"no CPU fallback" in sb.lib().sac_last_error()
+
+
+def test_base_profile_and_presets(golden):
+    vmin, vmax, vdef = sb.base_profile()
+    bp = golden["base_profile"]
+    assert np.array_equal(vdef, np.array(bp["vdef"], np.float32)) and np.array_equal(vmin, np.array(bp["vmin"], np.float32))
+    assert np.array_equal(vmax, np.array(bp["vmax"], np.float32))
+    c = sb.make_cfg("best")    # cmdline.cpp:145-150
+    assert (c.optimize, c.fraction, c.maxnfunc, c.sigma, c.cost_kind, c.optk) == (1, 0.5, 1000, 0.25, sb.COST_BITPLANE, 4)
+    c = sb.make_cfg("high")    # cmdline.cpp:129-134
+    assert (c.optimize, c.fraction, c.maxnfunc, c.sigma, c.cost_kind) == (1, 0.1, 100, 0.20, sb.COST_ENTROPY)
+    c = sb.make_cfg("normal")
+    assert c.optimize == 0 and c.max_framelen == 20 and c.zero_mean == 1
+
+
+def test_dds_driver_matches_reference_goldens(golden):
+    """sac_dds_run (product) against the traces recorded from the reference's OptDDS"""
+    vmin, vmax, vdef = sb.base_profile()
+    idx = sb.SEARCH_DIMS
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    for g in golden["dds"]:
+        trace = []
+
+        def f(X):
+            trace.extend(list(X))
+            z = (X - xmin) / (xmax - xmin)
+            return np.sum((z - 0.37) ** 2, axis=1) + 0.05 * np.sum(np.cos(9 * z), axis=1)
+
+        best, xb = sb.dds_run(f, xmin, xmax, xs, g["nfunc"], g["num_threads"], g["sigma"])
+        t = np.stack(trace)
+        assert len(t) == g["evals"]
+        assert sha(t[np.lexsort(t.T[::-1])]) == g["trace_sha1"]
+        assert sha(xb) == g["xbest_sha1"] and abs(best - g["best"]) <= 1e-12 * abs(g["best"])
+
+
+def test_model_tables_equal_reference_tables():
+    st = np.zeros(32768, np.int16); sq = np.zeros(4095, np.int16)
+    sb.lib().sac_model_tables(st.ctypes.data_as(C.c_void_p), sq.ctypes.data_as(C.c_void_p))
+    fwd = np.zeros(32768, np.int32); inv = np.zeros(4095, np.int32)
+    ol.oracle().saco_logdomain_tables(fwd.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(st.astype(np.int32), fwd) and np.array_equal(sq.astype(np.int32), inv)
+    ref = ol.ref_lib()
+    if ref is not None:
+        ref.ref_logdomain_tables(fwd.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(st.astype(np.int32), fwd) and np.array_equal(sq.astype(np.int32), inv)
+
+
+def test_product_does_not_reference_the_oracle():
+    """the shipped path must not import, link or execute anything under oracle/"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sac_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "liboracle" not in txt and "sac_oracle" not in txt and "oracle_lib" not in txt, fn
+    import subprocess
+    out = subprocess.run(["ldd", sb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
