@@ -16,6 +16,7 @@
 #include "bitplane.h"
 #include "sac_canon_math.h"
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 namespace sacb {
 
@@ -51,12 +52,13 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v,
 
 struct Tables { const int16_t *stretch; const int16_t *squash; const uint16_t *laplace; int lap_bits; };
 
-__device__ __forceinline__ int stretch(const Tables &T, int p) { return __ldg(T.stretch + p); }
+// stretch / squash point into the CTA's shared-memory copies (stage_tables): they sit on the serial chain of every decision
+__device__ __forceinline__ int stretch(const Tables &T, int p) { return T.stretch[p]; }
 __device__ __forceinline__ int squash(const Tables &T, int x)
 {
   if (x < -2047) return 1;
   if (x > 2047) return PSCALEm;
-  return __ldg(T.squash + (x + 2047));
+  return T.squash[x + 2047];
 }
 
 // LinearCounterLimit::update (counter.h:58-68)
@@ -243,15 +245,32 @@ __device__ __forceinline__ uint32_t scan_incl(uint32_t v, int lane)
 }
 __device__ __forceinline__ int topbit(uint32_t x) { return 31 - __clz(x); }   // -1 for 0
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = 2;
+constexpr int kStretchBytes = PSCALE * 2, kSquashBytes = 4096 * 2;   // shared-memory copies of the LogDomain tables
+
+// copies the LogDomain tables to the head of the CTA's dynamic shared memory; returns the table view to use
+__device__ __forceinline__ Tables stage_tables(const Tables &G, unsigned char *smem)
+{
+  const uint4 *gs = reinterpret_cast<const uint4 *>(G.stretch);
+  uint4 *ss = reinterpret_cast<uint4 *>(smem);
+  for (int i = threadIdx.x; i < kStretchBytes / 16; i += blockDim.x) ss[i] = __ldg(gs + i);
+  int16_t *sq = reinterpret_cast<int16_t *>(smem + kStretchBytes);
+  for (int i = threadIdx.x; i < 4095; i += blockDim.x) sq[i] = __ldg(G.squash + i);
+  __syncthreads();
+  Tables T = G;
+  T.stretch = reinterpret_cast<const int16_t *>(smem);
+  T.squash = sq;
+  return T;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // encoder / byte counter. One warp per job.
 template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_encode_kernel(const BpJob *__restrict__ jobs, int njobs, Tables T)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_encode_kernel(const BpJob *__restrict__ jobs, int njobs, Tables TG)
 {
   extern __shared__ __align__(16) unsigned char bp_smem[];
-  BpState *states = reinterpret_cast<BpState *>(bp_smem);
+  const Tables T = stage_tables(TG, bp_smem);
+  BpState *states = reinterpret_cast<BpState *>(bp_smem + kStretchBytes + kSquashBytes);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int job = blockIdx.x * kWarpsPerCta + wib;
   if (job >= njobs) return;
@@ -406,11 +425,379 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_encode_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// decoder: one warp per stream, each decision evaluated cooperatively (vle.cpp:233-261)
-__global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_decode_kernel(const BpJob *__restrict__ jobs, int njobs, Tables T)
+// Pipelined encoder / byte counter: one CTA (4 warps) per stream. The adaptive chain of a decision splits into four
+// recurrences that only feed forward, so each gets its own warp and they run one chunk (32 decisions) apart:
+//
+//   W1  contexts of the chunk (all lanes, as above) + the bit-driven counters and their stretch() inputs
+//   W2  logistic mixer (vle.cpp:120-129,166-175, mixer.h:59-101)
+//   W3  the two SSE stages (vle.cpp:188-197, sse.h:84-125)
+//   W4  final mixer + range coder (vle.cpp:197-204, range.cpp:66-92)
+//
+// Records travel through double-buffered rings in shared memory (one slot per decision, published per chunk).
+// Inside a warp the forward path is evaluated uniformly; the state updates of one decision (up to 5 counters,
+// 5 mixer weights, 4 SSE knots) are spread over lanes, one update each. Arithmetic is identical to model_step.
+struct PipeShared {
+  BpState st;
+  uint32_t mixpad[4];                                              // a sig-branch mixer reads weights [3],[4] (times 0)
+  uint16_t divtab[304];
+  uint32_t dummy;
+  uint4 r12[64];
+  uint2 r23[64];
+  uint2 r34[64];
+  int pub12, con12, pub23, con23, pub34, con34;
+  uint32_t red[4];
+};
+
+__device__ __forceinline__ int pld(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void pst(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ void pipe_wait_gt(const int *ctr, int v)
+{
+  while (pld(ctr) <= v) __nanosleep(40);
+  __threadfence_block();
+}
+__device__ __forceinline__ void pipe_publish(int *ctr, int v, int lane)
+{
+  __syncwarp();
+  __threadfence_block();
+  if (lane == 0) pst(ctr, v);
+}
+__device__ __forceinline__ int sx16(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+
+// LinearCounterLimit::update with the divisor table in shared memory (lanes update different counters)
+__device__ __forceinline__ uint32_t counter_upd_s(const uint16_t *divtab, uint32_t c, int bit, int limit)
+{
+  int p1 = (int)(c & 0xffffu), cnt = (int)(c >> 16);
+  if (cnt < limit) cnt++;
+  const int dv = divtab[cnt];
+  const int dp = bit ? ((PSCALE - p1) * dv) >> PBITS : -((p1 * dv) >> PBITS);
+  p1 = clampi(p1 + dp, 1, PSCALEm);
+  return (uint32_t)p1 | ((uint32_t)cnt << 16);
+}
+
+constexpr int kPipeThreads = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(kPipeThreads) bitplane_pipe_kernel(const BpJob *__restrict__ jobs, Tables TG)
 {
   extern __shared__ __align__(16) unsigned char bp_smem[];
-  BpState *states = reinterpret_cast<BpState *>(bp_smem);
+  const Tables T = stage_tables(TG, bp_smem);
+  PipeShared &P = *reinterpret_cast<PipeShared *>(bp_smem + kStretchBytes + kSquashBytes);
+  BpState &S = P.st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const BpJob J = jobs[blockIdx.x];
+  const int n = J.n;
+  int32_t *u = J.buf;
+
+  // ---- S2U map (utils.h:248-253) and maxbpn (libsac.cpp:429-441, cost.h:150-158), all threads ----
+  uint32_t vmax = 0;
+  if (J.signed_input) {
+    for (int i = tid; i < n; i += kPipeThreads) {
+      const int32_t v = u[i];
+      const int32_t m = v < 0 ? 2 * (-v) : (v > 0 ? 2 * v - 1 : 0);
+      u[i] = m;
+      vmax = max(vmax, (uint32_t)m);
+    }
+  } else {
+    for (int i = tid; i < n; i += kPipeThreads) vmax = max(vmax, (uint32_t)u[i]);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) vmax = max(vmax, __shfl_xor_sync(kFull, vmax, o));
+  if (lane == 0) P.red[warp] = vmax;
+  // ---- state ----
+  {
+    const uint32_t c0 = (uint32_t)(PSCALE >> 1);
+    for (int i = tid; i < 32; i += kPipeThreads) { S.plap[i] = c_plap_init[i]; S.cref0[i] = c0; }
+    for (int i = tid; i < 128; i += kPipeThreads) S.csig1[i] = c0;
+    for (int i = tid; i < 256; i += kPipeThreads) { S.cref1[i] = c0; S.cref3[i] = c0; }
+    for (int i = tid; i < 64; i += kPipeThreads) S.cref2[i] = c0;
+    for (int i = tid; i < 32 * 5; i += kPipeThreads) (&S.mixref[0][0])[i] = 0;
+    for (int i = tid; i < 128 * 3; i += kPipeThreads) (&S.mixsig[0][0])[i] = 0;
+    for (int i = tid; i < 160 * 32; i += kPipeThreads) (&S.sse[0][0][0])[i] = c_sse_init[i & 15];
+    for (int i = tid; i < 160; i += kPipeThreads) S.sse_lb[i] = 0;
+    for (int i = tid; i < 304; i += kPipeThreads) P.divtab[i] = c_div[i];
+    if (tid < 4) P.mixpad[tid] = 0;
+    if (tid == 0) { S.ssemix[0] = 0; S.ssemix[1] = 0; P.dummy = 0; P.pub12 = 0; P.con12 = 0; P.pub23 = 0; P.con23 = 0; P.pub34 = 0; P.con34 = 0; }
+    uint4 *c4 = reinterpret_cast<uint4 *>(J.csig0);
+    const uint4 v4 = make_uint4(c0, c0, c0, c0);
+    for (int i = tid; i < 65536 / 4; i += kPipeThreads) c4[i] = v4;
+  }
+  __syncthreads();
+  vmax = max(max(P.red[0], P.red[1]), max(P.red[2], P.red[3]));
+  const int maxbpn = J.maxbpn >= 0 ? J.maxbpn : max(topbit(vmax), 0);
+  const int nchunks = (n + 31) >> 5;
+  // mixer weights as one int array: mixref rows (5 ints) then mixsig rows (3 ints); BpState keeps them adjacent
+  int *mixw = &S.mixref[0][0];
+  constexpr int kSigBase = 32 * 5;
+
+  if (warp == 0) {
+    // ================================ W1: contexts + counters ======================================================
+    uint32_t *sw = &S.plap[0];                                     // plap | csig1 | cref0 | cref1 | cref2 | cref3 (adjacent)
+    constexpr int oCsig1 = 32, oCref0 = 160, oCref1 = 192, oCref2 = 448, oCref3 = 512;
+    const int oDummy = (int)(&P.dummy - sw);
+    int q = 0;
+    for (int bpn = maxbpn; bpn >= 0; bpn--) {
+      const int shA = bpn + 1, shB = max(bpn, 1);
+      const uint32_t himask = ~((2u << bpn) - 1u);
+      uint32_t u_prev = 0, u_cur = 0, u_next = lane < n ? (uint32_t)u[lane] : 0u;
+      uint32_t pre_cur = 0, tot_cur = 0, hi_cur = 0, suf_prev = 0;
+      uint32_t pre_next, tot_next;
+      {
+        const uint32_t h = u_next & himask;
+        pre_next = scan_incl(h, lane);
+        tot_next = __shfl_sync(kFull, pre_next, 31);
+      }
+      uint32_t A_prev = 0, A_cur = 0, A_next = __ballot_sync(kFull, (u_next >> shA) != 0);
+      uint32_t B_prev = 0, B_cur = 0;
+      uint32_t K_prev = 0, K_cur = 0;
+      for (int c = 0; c < nchunks; c++, q++) {
+        const int base = c << 5, s = base + lane;
+        suf_prev = tot_cur - pre_cur + hi_cur;
+        u_prev = u_cur; u_cur = u_next;
+        pre_cur = pre_next; tot_cur = tot_next; hi_cur = u_cur & himask;
+        A_prev = A_cur; A_cur = A_next; B_prev = B_cur; K_prev = K_cur;
+        {
+          const int sn = s + 32;
+          u_next = sn < n ? (uint32_t)u[sn] : 0u;
+          const uint32_t h = u_next & himask;
+          pre_next = scan_incl(h, lane);
+          tot_next = __shfl_sync(kFull, pre_next, 31);
+          A_next = __ballot_sync(kFull, (u_next >> shA) != 0);
+        }
+        B_cur = __ballot_sync(kFull, (u_cur >> shB) != 0);
+        K_cur = __ballot_sync(kFull, ((u_cur >> bpn) & 1u) != 0);
+        const unsigned long long AL = ((unsigned long long)A_cur << 32) | A_prev;
+        const unsigned long long BL = ((unsigned long long)B_cur << 32) | B_prev;
+        const unsigned long long KL = ((unsigned long long)K_cur << 32) | K_prev;
+        const unsigned long long AR = ((unsigned long long)A_next << 32) | A_cur;
+        const uint32_t a_left = (uint32_t)(AL >> lane), b_left = (uint32_t)(BL >> lane), k_left = (uint32_t)(KL >> lane);
+        const uint32_t a_right = (uint32_t)(AR >> (lane + 1));
+        uint32_t a_right_cnt = a_right;
+        { const int dl = (n - 1) - (s + 1); if (dl >= 0 && dl < 32) a_right_cnt &= ~(1u << dl); }
+        auto leftbit = [&](uint32_t wbits, int dd) { return (int)((wbits >> (32 - dd)) & 1u); };
+        auto rightbit = [&](uint32_t wbits, int dd) { return (int)((wbits >> (dd - 1)) & 1u); };
+        const int selfA = (int)((A_cur >> lane) & 1u);
+        const int bit_l = (int)((u_cur >> bpn) & 1u);
+        const uint32_t nsum = suf_prev + tot_cur + pre_next + ((uint32_t)__popc(k_left) << bpn);
+        const int nidx = min(s + 32, n - 1) - max(s - 32, 0) + 1;
+        const uint32_t avg = s < n ? (nsum + (uint32_t)(nidx - 1)) / (uint32_t)nidx : 0u;
+        const int pe_l = laplace_p(T, avg, bpn);
+        auto nb = [&](int dd) -> uint32_t {
+          const int sl = lane + dd;
+          const uint32_t vc = __shfl_sync(kFull, u_cur, sl & 31);
+          const uint32_t vp = __shfl_sync(kFull, u_prev, sl & 31);
+          const uint32_t vn = __shfl_sync(kFull, u_next, sl & 31);
+          return sl < 0 ? vp : (sl > 31 ? vn : vc);
+        };
+        const uint32_t l1 = nb(-1), l2 = nb(-2), l3 = nb(-3), l4 = nb(-4);
+        const uint32_t r1 = nb(1), r2 = nb(2), r3 = nb(3), r4 = nb(4);
+        uint32_t rec0, rec1, cs_val = 0;
+        const int sse2_l = 32 + selfA + (leftbit(b_left, 1) << 1) + (rightbit(a_right, 1) << 2) + (leftbit(b_left, 2) << 3) +
+                           (rightbit(a_right, 2) << 4) + (leftbit(b_left, 3) << 5) + (rightbit(a_right, 3) << 6);
+        rec0 = (uint32_t)pe_l | ((uint32_t)bit_l << 15) | ((uint32_t)selfA << 16) | ((uint32_t)sse2_l << 17);
+        if (selfA) {
+          const int b0 = (int)(u_cur >> (bpn + 1)), b1 = (int)(l1 >> bpn), b2 = (int)(r1 >> (bpn + 1));
+          const int b3 = (int)(l2 >> bpn), b4 = (int)(r2 >> (bpn + 1));
+          const int c0 = (b0 << 1) < b1, c1 = b0 < b2, c2 = (b0 << 1) < b3, c3 = b0 < b4;
+          const int x0 = b0 << 1, x1 = b1, x2 = b2 << 1, x3 = b3, x4 = b4 << 1;
+          const int xm = (x0 + x1 + x2 + x3 + x4) / 5;
+          const int d0 = x0 > xm, d1 = x1 > xm;
+          const int cc1 = (b0 & 15) + ((b1 & 15) << 4);
+          const int cc2 = (c0 + (c1 << 1) + (c2 << 2) + (c3 << 3)) + (d0 << 4) + (d1 << 5);
+          auto msbL = [&](uint32_t v) { return (v >> shB) != 0 ? topbit(v) : 0; };
+          auto msbR = [&](uint32_t v) { return (v >> shA) != 0 ? topbit(v) : 0; };
+          const int cc3 = msbL(l1) + msbR(r1) + msbL(l2) + msbR(r2) + msbL(l3) + msbR(r3) + msbL(l4) + msbR(r4);
+          const int pctx = ((((pe_l >> 12) << 1) + d0) << 1) + (b0 & 1);
+          rec1 = (uint32_t)topbit(u_cur) | ((uint32_t)cc1 << 5) | ((uint32_t)cc2 << 13) | ((uint32_t)cc3 << 19) | ((uint32_t)pctx << 27);
+        } else {
+          int ctx1 = 0;
+#pragma unroll
+          for (int dd = 1; dd <= 8; dd++) ctx1 |= (leftbit(b_left, dd) << (2 * dd - 2)) | (rightbit(a_right, dd) << (2 * dd - 1));
+          const int n1 = __popc(b_left) + __popc(a_right_cnt);
+          const int n2 = __popc(a_left) + __popc(a_right_cnt);
+          int st4 = 0;
+#pragma unroll
+          for (int dd = 1; dd <= 4; dd++) st4 |= ((s - dd >= 0 && !leftbit(a_left, dd)) ? 1 : 0) << (dd - 1);
+          const int mixctx = (st4 << 3) + (min(n1, 3) << 1) + (n2 > 0 ? 1 : 0);
+          rec1 = (uint32_t)ctx1 | ((uint32_t)n2 << 16) | ((uint32_t)mixctx << 23);
+          if (s < n) cs_val = J.csig0[ctx1];
+        }
+        // ---- ring slot free? then the serial part: counters of each decision, inputs to the mixer ----
+        if (q >= 2) pipe_wait_gt(&P.con12, q - 2);
+        uint4 *ring = P.r12 + ((q & 1) << 5);
+        const int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; j++) {
+          const uint32_t w0 = __shfl_sync(kFull, rec0, j), w1 = __shfl_sync(kFull, rec1, j);
+          const uint32_t cs = __shfl_sync(kFull, cs_val, j);
+          const int pe = (int)(w0 & 0x7fff), bit = (int)((w0 >> 15) & 1), is_ref = (int)((w0 >> 16) & 1), sse2 = (int)((w0 >> 17) & 0xff);
+          const int sse1 = ((pe >> 11) << 1) + is_ref;
+          // lane roles. lane 0: p_laplace[bpn]; ref: lanes 1-4 cref0..3, lane 6 carries pestimate; sig: lane 1 csig1, lanes >= 5 csig0
+          int off = oDummy, limit = kLimSig, pos = -1, woff;
+          if (is_ref) {
+            const int tb = (int)(w1 & 31), c1 = (int)((w1 >> 5) & 0xff), c2 = (int)((w1 >> 13) & 0x3f), c3 = (int)((w1 >> 19) & 0xff);
+            woff = (int)(w1 >> 27) * 5;
+            limit = kLimRef;
+            if (lane == 1) { off = oCref0 + tb; pos = 2; }
+            else if (lane == 2) { off = oCref1 + c1; pos = 3; }
+            else if (lane == 3) { off = oCref2 + c2; pos = 4; }
+            else if (lane == 4) off = oCref3 + c3;
+            else if (lane == 6) pos = 0;
+            if (lane == 0) pos = 1;
+          } else {
+            const int n2 = (int)((w1 >> 16) & 0x7f);
+            woff = kSigBase + (int)((w1 >> 23) & 0x7f) * 3;
+            if (lane == 1) { off = oCsig1 + n2; pos = 2; }
+            else if (lane == 2) pos = 3;
+            else if (lane == 3) pos = 4;
+            else if (lane == 5) pos = 1;
+            if (lane == 0) pos = 0;
+          }
+          if (lane == 0) { off = bpn; limit = kLimP; }
+          uint32_t v = sw[off];
+          if (lane >= 5) v = (is_ref && lane == 6) ? (uint32_t)pe : cs;
+          int sx = stretch(T, (int)(v & 0xffffu));
+          if (!is_ref && (lane == 2 || lane == 3)) sx = 0;
+          uint16_t *slot16 = reinterpret_cast<uint16_t *>(ring + j);
+          if (pos >= 0) slot16[pos] = (uint16_t)sx;
+          if (lane == 7) {
+            uint32_t *slot32 = reinterpret_cast<uint32_t *>(ring + j);
+            slot32[3] = (uint32_t)woff | ((uint32_t)is_ref << 10) | ((uint32_t)bit << 11) | ((uint32_t)sse1 << 12) | ((uint32_t)sse2 << 20);
+          }
+          const uint32_t nv = counter_upd_s(P.divtab, v, bit, limit);
+          if (lane < 5 && off != oDummy) sw[off] = nv;
+          if (!is_ref) {
+            const uint32_t csn = __shfl_sync(kFull, nv, 31);
+            const int ctx1 = (int)(w1 & 0xffff);
+            if (lane == 5) J.csig0[ctx1] = csn;
+            if (!selfA && lane > j && (int)(rec1 & 0xffff) == ctx1) cs_val = csn;   // keep prefetched copies coherent
+          }
+          __syncwarp();
+        }
+        pipe_publish(&P.pub12, q + 1, lane);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ W2: mixer =====================================================================
+    int q = 0;
+    for (int bpn = maxbpn; bpn >= 0; bpn--) {
+      for (int c = 0; c < nchunks; c++, q++) {
+        const int cnt = min(32, n - (c << 5));
+        pipe_wait_gt(&P.pub12, q);
+        if (q >= 2) pipe_wait_gt(&P.con23, q - 2);
+        const uint4 *rin = P.r12 + ((q & 1) << 5);
+        uint2 *rout = P.r23 + ((q & 1) << 5);
+        for (int j = 0; j < cnt; j++) {
+          const uint4 r = rin[j];
+          const int x0 = sx16(r.x), x1 = sx16(r.x >> 16), x2 = sx16(r.y), x3 = sx16(r.y >> 16), x4 = sx16(r.z);
+          const int woff = (int)(r.w & 0x3ff), is_ref = (int)((r.w >> 10) & 1), bit = (int)((r.w >> 11) & 1);
+          int *w = mixw + woff;
+          long long sum = (long long)(w[0] * x0) + (long long)(w[1] * x1) + (long long)(w[2] * x2);
+          if (is_ref) sum += (long long)(w[3] * x3) + (long long)(w[4] * x4);
+          const int p_mix = clampi(squash(T, idiv_s64(sum, 16)), 1, PSCALEm);
+          const int stp = stretch(T, p_mix);
+          if (lane == 0) rout[j] = make_uint2((uint32_t)p_mix | ((uint32_t)(stp & 0xffff) << 16), r.w >> 11);
+          const int err = (bit << PBITS) - p_mix;
+          const int rate = is_ref ? kRateRef : kRateSig;
+          const int nin = is_ref ? 5 : 3;
+          __syncwarp();                                            // every lane has read the weights
+          if (lane < nin) {
+            const int xi = lane == 0 ? x0 : (lane == 1 ? x1 : (lane == 2 ? x2 : (lane == 3 ? x3 : x4)));
+            const int de = idiv_s(xi * err, 12);
+            w[lane] = clampi(w[lane] + idiv_s(de * rate, 12), -(1 << 19), (1 << 19) - 1);
+          }
+          __syncwarp();
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) { pst(&P.con12, q + 1); pst(&P.pub23, q + 1); }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ W3: SSE =======================================================================
+    int q = 0;
+    for (int bpn = maxbpn; bpn >= 0; bpn--) {
+      for (int c = 0; c < nchunks; c++, q++) {
+        const int cnt = min(32, n - (c << 5));
+        pipe_wait_gt(&P.pub23, q);
+        if (q >= 2) pipe_wait_gt(&P.con34, q - 2);
+        const uint2 *rin = P.r23 + ((q & 1) << 5);
+        uint2 *rout = P.r34 + ((q & 1) << 5);
+        for (int j = 0; j < cnt; j++) {
+          const uint2 r = rin[j];
+          const int stp = sx16(r.x >> 16);
+          const int bit = (int)(r.y & 1), sse1 = (int)((r.y >> 1) & 0xff), sse2 = (int)((r.y >> 9) & 0xff);
+          const int lb1 = S.sse_lb[sse1], lb2 = S.sse_lb[sse2];
+          uint16_t *k1 = &S.sse[sse1][lb1][0], *k2 = &S.sse[sse2][lb2][0];
+          int q1, q2, pr1, pr2;
+          {
+            const int pq = min(2 * kTScale, max(0, stp + kTScale));
+            q1 = pq / kXScale;
+            const int pm = pq - q1 * kXScale;
+            const int pl = k1[q1], ph = k1[q1 + 1];
+            pr1 = clampi((pl * (kXScale - pm) + ph * pm) / kXScale, 1, PSCALEm);
+          }
+          {
+            const int pq = min(2 * kTScale, max(0, stretch(T, pr1) + kTScale));
+            q2 = pq / kXScale;
+            const int pm = pq - q2 * kXScale;
+            const int pl = k2[q2], ph = k2[q2 + 1];
+            pr2 = clampi((pl * (kXScale - pm) + ph * pm) / kXScale, 1, PSCALEm);
+          }
+          const int xs0 = stretch(T, (pr1 + pr2 + 1) >> 1);
+          if (lane == 0) rout[j] = make_uint2((uint32_t)(xs0 & 0xffff) | ((uint32_t)(stp & 0xffff) << 16), (uint32_t)bit);
+          __syncwarp();                                            // every lane has read the knots
+          if (lane < 4) {
+            uint16_t *kp = (lane < 2 ? k1 + q1 : k2 + q2) + (lane & 1);
+            *kp = (uint16_t)counter16_upd(*kp, bit, kRateSse);
+          } else if (lane == 4) S.sse_lb[sse1] = bit;
+          else if (lane == 5) S.sse_lb[sse2] = bit;
+          __syncwarp();
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) { pst(&P.con23, q + 1); pst(&P.pub34, q + 1); }
+      }
+    }
+  } else {
+    // ================================ W4: final mixer + coder =======================================================
+    Coder rc;
+    rc.range = 0xFFFFFFFFu; rc.ffnum = 0; rc.cache = 0; rc.lowc = 0; rc.nbytes = 0; rc.out = J.out;
+    int m0 = 0, m1 = 0;
+    int q = 0;
+    for (int bpn = maxbpn; bpn >= 0; bpn--) {
+      for (int c = 0; c < nchunks; c++, q++) {
+        const int cnt = min(32, n - (c << 5));
+        pipe_wait_gt(&P.pub34, q);
+        const uint2 *rin = P.r34 + ((q & 1) << 5);
+        const uint2 mine = lane < cnt ? rin[lane] : make_uint2(0u, 0u);
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) pst(&P.con34, q + 1);                       // records are in registers now
+        for (int j = 0; j < cnt; j++) {
+          const uint32_t rx = __shfl_sync(kFull, mine.x, j), ry = __shfl_sync(kFull, mine.y, j);
+          const int xs0 = sx16(rx), xs1 = sx16(rx >> 16), bit = (int)(ry & 1);
+          const int pfin = clampi(squash(T, idiv_s64((long long)(m0 * xs0) + (long long)(m1 * xs1), 16)), 1, PSCALEm);
+          rc_encode<MODE>(rc, pfin, bit, lane);
+          const int err = (bit << PBITS) - pfin;
+          m0 = clampi(m0 + idiv_s(idiv_s(xs0 * err, 12) * kRateSseMix, 12), -(1 << 19), (1 << 19) - 1);
+          m1 = clampi(m1 + idiv_s(idiv_s(xs1 * err, 12) * kRateSseMix, 12), -(1 << 19), (1 << 19) - 1);
+        }
+      }
+    }
+    for (int i = 0; i < 5; i++) shift_low<MODE>(rc, lane);         // RangeCoderSH::Stop (range.cpp:61-64)
+    if (lane == 0) {
+      if (J.nbytes) *J.nbytes = rc.nbytes;
+      if (J.maxbpn_out) *J.maxbpn_out = maxbpn;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decoder: one warp per stream, each decision evaluated cooperatively (vle.cpp:233-261)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_decode_kernel(const BpJob *__restrict__ jobs, int njobs, Tables TG)
+{
+  extern __shared__ __align__(16) unsigned char bp_smem[];
+  const Tables T = stage_tables(TG, bp_smem);
+  BpState *states = reinterpret_cast<BpState *>(bp_smem + kStretchBytes + kSquashBytes);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int job = blockIdx.x * kWarpsPerCta + wib;
   if (job >= njobs) return;
@@ -573,7 +960,7 @@ cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int n
 {
   Tables T{bt.d_stretch, bt.d_squash, bt.d_laplace, bt.lap_bits};
   const int grid = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
-  const int smem = (int)(sizeof(BpState) * kWarpsPerCta);
+  const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
   static bool attr = false;
   if (!attr) {
     cudaError_t e;
@@ -581,6 +968,20 @@ cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int n
     if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bitplane_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
     attr = true;
+  }
+  static const bool use_pipe = !(getenv("SAC_B200_BP_PIPE") && atoi(getenv("SAC_B200_BP_PIPE")) == 0);
+  if (mode != 2 && use_pipe) {
+    const int psmem = (int)sizeof(PipeShared) + kStretchBytes + kSquashBytes;
+    static bool pattr = false;
+    if (!pattr) {
+      cudaError_t e;
+      if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
+      pattr = true;
+    }
+    if (mode == 0) bitplane_pipe_kernel<0><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
+    else bitplane_pipe_kernel<1><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
+    return cudaGetLastError();
   }
   if (mode == 0) bitplane_encode_kernel<0><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);
   else if (mode == 1) bitplane_encode_kernel<1><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);

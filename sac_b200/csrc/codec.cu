@@ -190,7 +190,10 @@ int wav_parse(const uint8_t *f, size_t len, WavInfo &wi)
         if (endofdata > len) wi.numsamples = (uint32_t)((len - pos) / wi.blockalign);   // truncated data chunk (wav.cpp:238-243)
         break;
       }
-      pos += cs;                                                       // (the reference seeks by chunksize, not the aligned size)
+      // Deliberate deviation: the reference seeks by chunksize (wav.cpp:246-247), which lands on the pad byte of an
+      // odd-sized data chunk and misparses every chunk after it; its own decoder re-inserts that pad byte
+      // (libsac.cpp:880-881), so the aligned skip is what round-trips.
+      pos += word_align(cs);
     } else {
       const uint32_t rs = word_align(cs);
       if (pos + rs > len) { set_error("truncated wav chunk"); return SAC_E_FORMAT; }

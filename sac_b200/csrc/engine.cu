@@ -74,7 +74,8 @@ long long chain_scratch_doubles(const HostParam &hp, int cc, int)
   for (int s = 0; s < 4; s++) t += 4LL * hp.vn[cc][s] + 1;
   const long long n = ols_order(hp, cc);
   t += (n + 1) * (n + 2);
-  return t + 8;
+  // the encode-direction kernel has its own layout; reserve for whichever is larger
+  return std::max(t + 8, predictor_enc_scratch_doubles(hp.vn[cc], (int)n));
 }
 
 int fill_chain(ChainDesc &d, const HostParam &hp, int nch, int cc, int k, const int32_t *const *planes, int from, int n,
@@ -127,6 +128,7 @@ int Engine::init(int dev)
   SACB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
+  if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   SACB_CUDA(bt.init(stream));
   return SAC_OK;
 }
@@ -186,7 +188,7 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   }
   SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor(d_descs.p, nchains, smem_bytes, false, stream));
+  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, stream));
   SACB_CUDA(cudaEventRecord(ev[1], stream));
   launches++; last_launches[0]++;
   return SAC_OK;

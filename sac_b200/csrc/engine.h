@@ -69,7 +69,8 @@ struct Engine {           // sac_engine
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   BitplaneTables bt;
-  int smem_bytes = 72 * 1024;
+  int smem_bytes = 72 * 1024;        // decode-direction kernel (predictor.cu)
+  int enc_smem_bytes = 100 * 1024;   // encode-direction kernel (predictor_enc.cu): 2 CTAs per SM
   long long launches = 0;
   double last_ms[3] = {0, 0, 0};
   long long last_launches[3] = {0, 0, 0};
@@ -103,6 +104,9 @@ struct Engine {           // sac_engine
 
 // kernels (predictor.cu, cost.cu)
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream);
+long long predictor_enc_scratch_doubles(const int *vn, int n_ols);
+size_t predictor_enc_shared_bytes();
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream);
 cudaError_t launch_dfma_peak(double *out, int blocks, int iters, cudaStream_t stream);

@@ -1,0 +1,833 @@
+// predictor_enc.cu -- encode-direction predictor as a pipeline of specialised warps (sm_100a).
+//
+// In the encoder the per-sample recurrence of one chain (OLS -> NLMS cascade + RLS -> mix -> bias, the reference's
+// Predictor for one coded channel, /root/reference src/libsac/pred.cpp:4-45) falls apart into three feed-forward
+// recurrences, because every stage is driven by *input* samples (teacher forcing):
+//
+//   OLS  (ols.cpp)                  p_lpc(t)            depends on inputs only
+//   cascade (cascade.h, ls.h, rls)  p_lms(t)            depends on inputs and p_lpc
+//   bias (bias.h) + residual        e(t)                depends on inputs and p_lpc + p_lms
+//
+// One CTA (256 threads) runs one chain; its eight warps are
+//
+//   warps 0-3  tap warps   128 lane-strided NLMS taps x 4 stages. Weights, power table and mu table of the first
+//                          kR0/kR1/kR2/kR3 x 128 taps of each stage live in REGISTERS (setmaxnreg.inc 176), the
+//                          history ring in shared memory; longer stages continue from shared memory / HBM scratch.
+//   warp 4     S  cascade scalars: stage predictions, 2-expert mix, stage targets, NLMS gradients, mix update
+//   warp 5     O  OLS: regressors, k predictions per block from a register-resident w, IRLS weights, covariance
+//                 update (k rank-1 updates applied per element in one pass), look-ahead LDL^T, back substitution
+//   warp 6     B  bias stage, rounding, residual, cost sums
+//   warp 7     R  RLS stage (5th cascade stage)
+//
+// O -> S and S -> B are rings in shared memory (depth 32) so that O runs ahead by a whole solve block and B trails;
+// taps <-> S and S <-> R meet at named barriers (bar.arrive / bar.sync) twice per sample.
+//
+// The arithmetic is the canonical order of DESIGN.md section 2 (identical to predictor.cu, which remains the
+// decode-direction kernel): results are bit-identical to oracle/sac_oracle.cpp in SACO_ORDER_B200 / SACO_MATH_CANON.
+// Reference behaviour restated: src/libsac/pred.cpp:4-45, src/pred/{ols.cpp,ls.h,cascade.h,blend.h,rls.cpp,rls.h,
+// bias.h}, src/common/math.h:14-78, src/libsac/libsac.cpp:94-142.
+#include "chain.h"
+#include "sac_canon_math.h"
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <cstddef>
+
+namespace sacb {
+
+using sac_canon::c_exp;
+using sac_canon::c_pow;
+using sac_canon::c_round;
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kEncThreads = 384;                        // 3 warpgroups: taps | S, B, R | OLS team
+constexpr int kTeam = 128;
+constexpr int kR0 = 10, kR1 = 2, kR2 = 1, kR3 = 1;   // register-resident tap slots per thread and stage
+constexpr int kQ = 32;                                // ring depth (samples)
+constexpr int kXW = 256;                              // input window (samples, power of two)
+constexpr int kXS = 100;                              // row stride of the regressor block
+constexpr int kKB = 4;                                // samples per OLS sub-block
+enum { kBarB1 = 1, kBarB2 = 2, kBarB3 = 3, kBarB4 = 4, kBarT = 5 };
+
+__device__ __forceinline__ void bar_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+__device__ __forceinline__ double shfl_idx(double v, int l) { return __shfl_sync(kFull, v, l); }
+__device__ __forceinline__ double butterfly(double v)
+{
+  v = v + shfl_xor(v, 16);
+  v = v + shfl_xor(v, 8);
+  v = v + shfl_xor(v, 4);
+  v = v + shfl_xor(v, 2);
+  v = v + shfl_xor(v, 1);
+  return v;
+}
+__device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+__device__ __forceinline__ double dmax(double a, double b) { return a < b ? b : a; }  // std::max(a,b)
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }  // std::min(a,b)
+
+// slmath::dot for n < 8 and the AVX2 layout for 8 <= n <= 11 (math.h:130-161)
+__device__ double small_dot(const double *x, const double *y, int n)
+{
+  double total = 0.0;
+  int i = 0;
+  if (n >= 8) {
+    double s[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) s[l] = __fma_rn(x[l], y[l], 0.0) + __fma_rn(x[4 + l], y[4 + l], 0.0);
+    total = s[0] + s[1] + s[2] + s[3];
+    i = 8;
+  }
+  double init = 0.0;
+  while (n - i >= 4) {
+    const double v1 = x[i] * y[i] + x[i + 1] * y[i + 1];
+    const double v2 = x[i + 2] * y[i + 2] + x[i + 3] * y[i + 3];
+    init = init + (v1 + v2);
+    i += 4;
+  }
+  for (; i < n; i++) init = init + x[i] * y[i];
+  return total + init;
+}
+__device__ __forceinline__ double dot5(const double (&x)[kMixN], const double *y)
+{
+  const double v1 = x[0] * y[0] + x[1] * y[1];
+  const double v2 = x[2] * y[2] + x[3] * y[3];
+  double init = 0.0 + (v1 + v2);
+  init = init + x[4] * y[4];
+  return 0.0 + init;
+}
+
+struct EncShared {
+  // taps <-> S
+  double part[kTapWarps][8];          // [warp][stage] dot, [warp][4+stage] power sum
+  double wgrad[kStages];
+  double p[kMixN], spow[kStages];
+  // S: mix state (cascade.h:11-57, ls.h:214-241, blend.h)
+  double v[2][kMixN], eg[2][kMixN], sw[2], rsum[2];
+  // S <-> R
+  double bp4, p_rls;
+  // R: RLS state (rls.cpp)
+  double rx[kMaxRls], rw[kMaxRls], rph[kMaxRls], rP[kMaxRls][kMaxRls];
+  double S0, S1;
+  // B: bias state (bias.h)
+  double hist_in[8], hist_d[8], mixw[4][3];
+  double cnt[3][64], cval[3][64];
+  double bmean, bvar;
+  // O: regressor block and input windows
+  double X[kKB][kXS];
+  double xo[kXW], xq[kXW];
+  double pu[kKB], ff[kKB], wv[kMaxOls];
+  // rings
+  double q1[kQ], q2[kQ];
+  int q1_pub, q1_con, q2_pub, q2_con;
+  // layout
+  double *h[kStages], *ow[kStages], *opw[kStages], *omu[kStages];
+  double *fpw[kStages], *fmu[kStages];   // full tables (HBM scratch), used at start-up only
+  double sum_pow[kStages];
+  double *cov, *W;
+  int ld;
+};
+
+__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ double ldd_vol(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+__device__ __forceinline__ void spin_until_gt(const int *ctr, int v)
+{
+  while (ld_vol(ctr) <= v) __nanosleep(20);
+  __threadfence_block();                                     // acquire: ring data is read after the counter
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// tap warps
+template <int R> struct TapRegs { double w[R], pw[R], mu[R]; };
+
+template <int R>
+__device__ __forceinline__ void tap_load(TapRegs<R> &r, const double *fpw, const double *fmu, int N, int tl)
+{
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    const int i = tl + kTapThreads * j;
+    r.w[j] = 0.0;
+    r.pw[j] = i < N ? fpw[i] : 0.0;
+    r.mu[j] = i < N ? fmu[i] : 0.0;
+  }
+}
+
+// phase A: chain tl accumulates taps tl, tl+128, ... in ascending order (canonical order)
+template <int R>
+__device__ __forceinline__ void tap_dot(const TapRegs<R> &r, const double *h, const double *ow, const double *opw, int N, int pos,
+                                        int tl, double &ad, double &ap)
+{
+  const int cap = N + 1;
+  int hi = pos + tl;
+  if (hi >= cap) hi -= cap;
+  ad = 0.0; ap = 0.0;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    if (tl + kTapThreads * j < N) {
+      const double hv = h[hi];
+      ad = __fma_rn(hv, r.w[j], ad);
+      ap = __fma_rn(r.pw[j], hv * hv, ap);
+      hi += kTapThreads;
+      if (hi >= cap) hi -= cap;
+    }
+  }
+  for (int i = tl + kTapThreads * R; i < N; i += kTapThreads) {
+    const double hv = h[hi];
+    const int o = i - kTapThreads * R;
+    ad = __fma_rn(hv, ow[o], ad);
+    ap = __fma_rn(opw[o], hv * hv, ap);
+    hi += kTapThreads;
+    if (hi >= cap) hi -= cap;
+  }
+}
+
+// phase C: w_i = clamp(fma(mutab_i, wgrad*h_i, w_i), +-10) on the pre-push window (ls.h:49-54)
+template <int R>
+__device__ __forceinline__ void tap_update(TapRegs<R> &r, const double *h, double *ow, const double *omu, int N, int pos, int tl,
+                                           double g)
+{
+  const int cap = N + 1;
+  int hi = pos + tl;
+  if (hi >= cap) hi -= cap;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    if (tl + kTapThreads * j < N) {
+      const double tt = g * h[hi];
+      double wn = __fma_rn(r.mu[j], tt, r.w[j]);
+      wn = dmin(dmax(wn, -10.0), 10.0);
+      r.w[j] = wn;
+      hi += kTapThreads;
+      if (hi >= cap) hi -= cap;
+    }
+  }
+  for (int i = tl + kTapThreads * R; i < N; i += kTapThreads) {
+    const int o = i - kTapThreads * R;
+    const double tt = g * h[hi];
+    double wn = __fma_rn(omu[o], tt, ow[o]);
+    wn = dmin(dmax(wn, -10.0), 10.0);
+    ow[o] = wn;
+    hi += kTapThreads;
+    if (hi >= cap) hi -= cap;
+  }
+}
+
+__device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int tid)
+{
+  const int tl = tid, lane = tid & 31, tw = tid >> 5;
+  const int n = d.n;
+  const int N0 = d.vn[0], N1 = d.vn[1], N2 = d.vn[2], N3 = d.vn[3];
+  const double *h0 = S.h[0], *h1 = S.h[1], *h2 = S.h[2], *h3 = S.h[3];
+  double *ow0 = S.ow[0], *ow1 = S.ow[1], *ow2 = S.ow[2], *ow3 = S.ow[3];
+  const double *opw0 = S.opw[0], *opw1 = S.opw[1], *opw2 = S.opw[2], *opw3 = S.opw[3];
+  const double *omu0 = S.omu[0], *omu1 = S.omu[1], *omu2 = S.omu[2], *omu3 = S.omu[3];
+  TapRegs<kR0> r0; TapRegs<kR1> r1; TapRegs<kR2> r2; TapRegs<kR3> r3;
+  tap_load(r0, S.fpw[0], S.fmu[0], N0, tl);
+  tap_load(r1, S.fpw[1], S.fmu[1], N1, tl);
+  tap_load(r2, S.fpw[2], S.fmu[2], N2, tl);
+  tap_load(r3, S.fpw[3], S.fmu[3], N3, tl);
+  int p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  for (int t = 0; t < n; t++) {
+    double acc[8];
+    tap_dot(r0, h0, ow0, opw0, N0, p0, tl, acc[0], acc[4]);
+    tap_dot(r1, h1, ow1, opw1, N1, p1, tl, acc[1], acc[5]);
+    tap_dot(r2, h2, ow2, opw2, N2, p2, tl, acc[2], acc[6]);
+    tap_dot(r3, h3, ow3, opw3, N3, p3, tl, acc[3], acc[7]);
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = butterfly(acc[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) S.part[tw][q] = acc[q];
+    }
+    __threadfence_block();
+    bar_arrive(kBarB1, 160);
+    bar_sync(kBarB2, 160);
+    const double g0 = ldd_vol(&S.wgrad[0]), g1 = ldd_vol(&S.wgrad[1]), g2 = ldd_vol(&S.wgrad[2]), g3 = ldd_vol(&S.wgrad[3]);
+    tap_update(r0, h0, ow0, omu0, N0, p0, tl, g0);
+    tap_update(r1, h1, ow1, omu1, N1, p1, tl, g1);
+    tap_update(r2, h2, ow2, omu2, N2, p2, tl, g2);
+    tap_update(r3, h3, ow3, omu3, N3, p3, tl, g3);
+    p0 = p0 == 0 ? N0 : p0 - 1;                              // S pushed bp[s] at this slot
+    p1 = p1 == 0 ? N1 : p1 - 1;
+    p2 = p2 == 0 ? N2 : p2 - 1;
+    p3 = p3 == 0 ? N3 : p3 - 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// S: cascade scalars (cascade.h:91-118, ls.h:45-56 gradient, ls.h:223-237, blend.h:50-90)
+__device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n;
+  const double alpha = d.proj_alpha;
+  const int myN = lane < kStages ? d.vn[lane] : 0;
+  double *myh = lane < kStages ? S.h[lane] : nullptr;
+  const double my_mu = lane < kStages ? d.vmu[lane] : 0.0;
+  const double my_sp = lane < kStages ? S.sum_pow[lane] : 0.0;
+  int pos = 0;
+  bool bad = false;
+  int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
+  int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
+  for (int t = 0; t < n; t++) {
+    if ((t & 31) == 0 && t) { vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0; }
+    const double val = (double)__shfl_sync(kFull, vcur, t & 31);
+    // state that does not depend on this sample's predictions
+    const double sw0 = S.sw[0], sw1 = S.sw[1];
+    double v0[kMixN], v1[kMixN], wi[kMixN];
+#pragma unroll
+    for (int i = 0; i < kMixN; i++) {
+      v0[i] = S.v[0][i]; v1[i] = S.v[1][i];
+      wi[i] = dmax(0.0 + ((0.0 + v0[i] * sw0) + v1[i] * sw1), 0.0);
+    }
+    spin_until_gt(&S.q1_pub, t);
+    const double p_lpc = ldd_vol(&S.q1[t & (kQ - 1)]);
+    __syncwarp();
+    if (lane == 0) st_vol(&S.q1_con, t + 1);
+    const double target = val - p_lpc;
+    if (t) bar_sync(kBarB4, 64);                             // p_rls for this sample
+    bar_sync(kBarB1, 160);                                   // tap partial sums
+    if (lane < 8) {
+      const double v = (ldd_vol(&S.part[0][lane]) + ldd_vol(&S.part[1][lane])) + (ldd_vol(&S.part[2][lane]) + ldd_vol(&S.part[3][lane]));
+      if (lane < 4) S.p[lane] = v; else S.spow[lane - 4] = v;
+    }
+    if (lane == 8) S.p[4] = t ? ldd_vol(&S.p_rls) : 0.0;
+    __syncwarp();
+    double p[kMixN];
+#pragma unroll
+    for (int i = 0; i < kMixN; i++) p[i] = S.p[i];
+    // ---- mix predict (cascade.h:36-44, blend.h:25-30) ----
+    const double ep0 = dot5(p, v0), ep1 = dot5(p, v1);
+    if (!(fabs(ep0) <= 1.7976931348623157e308) || !(fabs(ep1) <= 1.7976931348623157e308)) bad = true;
+    const double p_lms = 0.0 + ((0.0 + ep0 * sw0) + ep1 * sw1);
+    const double px = p_lpc + p_lms;
+    // ---- stage targets (cascade.h:99-113) ----
+    double bp[kMixN];
+    {
+      double prefix = 0.0;
+#pragma unroll
+      for (int i = 0; i < kMixN; i++) {
+        const double pxi = (1.0 - alpha) * prefix + alpha * p_lms;
+        bp[i] = target - dmin(dmax(pxi, d.casc_lo), d.casc_hi);
+        prefix += wi[i] * p[i];
+      }
+    }
+    // ---- NLMS gradients + history push (ls.h:45-56) ----
+    if (lane < kStages) {
+      double bpl = bp[0], pl = p[0];
+      if (lane == 1) { bpl = bp[1]; pl = p[1]; } else if (lane == 2) { bpl = bp[2]; pl = p[2]; } else if (lane == 3) { bpl = bp[3]; pl = p[3]; }
+      S.wgrad[lane] = my_mu * (bpl - pl) * my_sp / (S.spow[lane] + 1.0);
+      const int np = pos == 0 ? myN : pos - 1;
+      myh[np] = bpl;
+      pos = np;
+    }
+    if (lane == 4) S.bp4 = bp[4];
+    __threadfence_block();
+    bar_arrive(kBarB2, 160);
+    bar_arrive(kBarB3, 64);
+    // ---- hand px to the bias warp ----
+    if (t >= kQ) spin_until_gt(&S.q2_con, t - kQ);
+    if (lane == 0) { S.q2[t & (kQ - 1)] = px; __threadfence_block(); st_vol(&S.q2_pub, t + 1); }
+    // ---- mix update: LS_ADA<L1>, LS_ADA<L2> (ls.h:223-237), BlendExp (blend.h:50-90) ----
+    {
+      if (lane < 2 * kMixN) {
+        const int ex = lane / kMixN, i = lane - ex * kMixN;
+        const double er = target - (ex == 0 ? ep0 : ep1);
+        const double loss = ex == 0 ? sgn(er) : er;
+        double pi_ = p[0];
+        if (i == 1) pi_ = p[1]; else if (i == 2) pi_ = p[2]; else if (i == 3) pi_ = p[3]; else if (i == 4) pi_ = p[4];
+        const double grad = loss * pi_;
+        const double egn = d.mix_beta * S.eg[ex][i] + (1.0 - d.mix_beta) * grad * grad;
+        S.eg[ex][i] = egn;
+        const double mu_scaled = d.mu_mix / (sqrt(egn) + 1e-5);
+        S.v[ex][i] += mu_scaled * grad;
+      }
+      const double r0 = 0.95 * S.rsum[0] + (1.0 - 0.95) * (-fabs(target - ep0));
+      const double r1 = 0.95 * S.rsum[1] + (1.0 - 0.95) * (-fabs(target - ep1));
+      const double z0 = 1.0 * r0, z1 = 1.0 * r1;
+      const double mz = dmax(dmax(-CUDART_INF, z0), z1);
+      const double w0 = c_exp(z0 - mz), w1 = c_exp(z1 - mz);
+      double total = 0.0; total += w0; total += w1;
+      const double inv_total = 1.0 / total;
+      __syncwarp();
+      if (lane == 0) { S.rsum[0] = r0; S.rsum[1] = r1; S.sw[0] = w0 * inv_total; S.sw[1] = w1 * inv_total; }
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && d.flags) *d.flags = bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// R: RLS stage, UpdateHist(bp[4]) then the prediction for t+1 (rls.cpp:17-65, rls.h:22-36)
+__device__ __forceinline__ void rls_warp(EncShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n, lm_n = d.lm_n;
+  double p_rls = 0.0;
+  for (int t = 0; t < n; t++) {
+    bar_sync(kBarB3, 64);
+    const double bp4 = ldd_vol(&S.bp4);
+    const double err = bp4 - p_rls;
+    if (lane < lm_n) S.rph[lane] = small_dot(S.rP[lane], S.rx, lm_n);
+    __syncwarp();
+    const double phi = dmax(small_dot(S.rx, S.rph, lm_n), 1e-8);
+    const double err2 = err * err;
+    const double R = dmax(S.S0 - S.S1, 1e-5);
+    const double nis = err2 / (phi + R);
+    const double m = c_exp(-d.lm_gamma * nis);
+    const double al = 0.99 + (0.999 - 0.99) * m;
+    const double denom = 1. / (al + phi);
+    const double inv_al = 1.0 / al;
+    for (int q = lane; q < lm_n * lm_n; q += 32) {
+      const int i = q / lm_n, j = q - i * lm_n;
+      if (j <= i) {
+        const double mm = S.rph[i] * S.rph[j];
+        const double vv = (S.rP[i][j] - denom * mm) * inv_al;
+        S.rP[i][j] = vv; S.rP[j][i] = vv;
+      }
+    }
+    double xprev = 0.0;
+    if (lane < lm_n) {
+      S.rw[lane] += err * (denom * S.rph[lane]);
+      xprev = lane > 0 ? S.rx[lane - 1] : bp4;
+    }
+    __syncwarp();
+    if (lane < lm_n) S.rx[lane] = xprev;                     // RollBack (utils.h:330-336)
+    if (lane == 0) {
+      S.S0 = 0.95 * S.S0 + (1.0 - 0.95) * err2;
+      S.S1 = 0.95 * S.S1 + (1.0 - 0.95) * phi;
+    }
+    __syncwarp();
+    p_rls = small_dot(S.rx, S.rw, lm_n);
+    if (t + 1 < n) {
+      if (lane == 0) S.p_rls = p_rls;
+      __threadfence_block();
+      bar_arrive(kBarB4, 64);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// B: bias stage (bias.h:64-162), round / clamp / residual (libsac.cpp:105-108), cost sums
+__device__ __forceinline__ void bias_warp(EncShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n;
+  long long l1 = 0, sq = 0;
+  int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
+  int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
+  int32_t ebuf = 0;
+  for (int t = 0; t < n; t++) {
+    if ((t & 31) == 0 && t) { vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0; }
+    const int32_t vali = __shfl_sync(kFull, vcur, t & 31);
+    const double val = (double)vali;
+    spin_until_gt(&S.q2_pub, t);
+    const double px = ldd_vol(&S.q2[t & (kQ - 1)]);
+    __syncwarp();
+    if (lane == 0) st_vol(&S.q2_con, t + 1);
+    // ---- bias predict (bias.h:64-126) ----
+    int ctx0, ctx1, ctx2, mix_ctx;
+    {
+      const double h0 = S.hist_in[0], h1 = S.hist_in[1], h2 = S.hist_in[2];
+      const double d0 = S.hist_d[0], d1 = S.hist_d[1], d2 = S.hist_d[2], d3 = S.hist_d[3], d4 = S.hist_d[4];
+      const int b0 = h0 > px ? 0 : 1;
+      const int b2 = d0 < 0 ? 0 : 1, b3 = d1 < 0 ? 0 : 1, b4 = d2 < 0 ? 0 : 1;
+      const int b5 = d1 < d0 ? 0 : 1, b6 = d2 < d1 ? 0 : 1, b7 = d3 < d2 ? 0 : 1, b8 = d4 < d3 ? 0 : 1;
+      const int b9 = fabs(d0) > 32 ? 0 : 1;
+      const int b10 = 2 * h0 - h1 > px ? 0 : 1;
+      const int b11 = 3 * h0 - 3 * h1 + h2 > px ? 0 : 1;
+      double sum = 0;
+      sum += fabs(d0); sum += fabs(d1); sum += fabs(d2); sum += fabs(d3); sum += fabs(d4);
+      sum /= 5.0;
+      mix_ctx = sum > 512 ? 2 : (sum > 32 ? 1 : 0);
+      ctx0 = b0 + (b2 << 1) + (b9 << 2) + (b10 << 3) + (b11 << 4);
+      ctx1 = b2 + (b3 << 1) + (b4 << 2);
+      ctx2 = b5 + (b6 << 1) + (b7 << 2) + (b8 << 3);
+    }
+    const int myctx = lane == 0 ? ctx0 : (lane == 1 ? ctx1 : ctx2);
+    double ptl = 0.0;
+    if (lane < 3) ptl = S.cval[lane][myctx] / S.cnt[lane][myctx];
+    const double pt0 = shfl_idx(ptl, 0), pt1 = shfl_idx(ptl, 1), pt2 = shfl_idx(ptl, 2);
+    const double pbias = 0.0 + (((0.0 + pt0 * S.mixw[mix_ctx][0]) + pt1 * S.mixw[mix_ctx][1]) + pt2 * S.mixw[mix_ctx][2]);
+    const double pd = px + pbias;
+    int32_t pi;
+    {
+      const double r = c_round(pd);
+      if (!(r >= (double)d.clamp_lo)) pi = d.clamp_lo;
+      else if (r > (double)d.clamp_hi) pi = d.clamp_hi;
+      else pi = (int32_t)r;
+    }
+    const int32_t e = vali - pi;
+    if ((t & 31) == lane) ebuf = e;
+    if ((t & 31) == 31 || t == n - 1) {
+      const int base = t & ~31;
+      if (base + lane <= t) d.resid[base + lane] = ebuf;
+    }
+    { const long long ae = e < 0 ? -(long long)e : (long long)e; l1 += ae; sq += (long long)e * (long long)e; }
+    // ---- bias update (bias.h:127-162) ----
+    {
+      const double delta = val - c_round(px);
+      const double bv = dmax(0.0, S.bvar), bm = S.bmean;
+      const double diff = delta - bm;
+      const double z = diff * diff / (bv + 1E-5);
+      const double wgt = c_exp(-0.5 * z);
+      double hin = 0.0, hdl = 0.0;
+      if (lane < 8) { hin = lane > 0 ? S.hist_in[lane - 1] : val; hdl = lane > 0 ? S.hist_d[lane - 1] : delta; }
+      __syncwarp();
+      if (lane < 8) { S.hist_in[lane] = hin; S.hist_d[lane] = hdl; }
+      if (lane < 3) {
+        double cv = S.cval[lane][myctx] + wgt * delta;
+        double cc = S.cnt[lane][myctx] + wgt;
+        if (cc >= (double)d.bias_nscale) { cv *= 0.5; cc *= 0.5; }
+        S.cval[lane][myctx] = cv; S.cnt[lane][myctx] = cc;
+        const double ptv = lane == 0 ? pt0 : (lane == 1 ? pt1 : pt2);
+        S.mixw[mix_ctx][lane] += (d.bias_mu * sgn(delta - pbias)) * sgn(ptv);
+      }
+      if (lane == 0) {
+        const double nm = 0.998 * bm + (1.0 - 0.998) * delta;
+        S.bvar = 0.998 * S.bvar + (1.0 - 0.998) * ((delta - bm) * (delta - nm));
+        S.bmean = nm;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    if (d.l1sum) *d.l1sum = l1;
+    if (d.sqsum) *d.sqsum = sq;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// O: OLS (ols.cpp:7-57, math.h:14-78) on a team of four warps (128 lanes, own named barrier). Matrices are
+// (n+1) x ld row-major squares: the lower triangle holds the covariance (row n = b) resp. the work matrix, the upper
+// triangle of the work matrix receives L^T. A block of k samples: regressors (all lanes) -> one prediction per warp
+// -> publish -> IRLS weights (one power per warp) -> covariance, k rank-1 updates per element in one pass, 8 x 16
+// lane grid -> LDL^T with the next pivot and its reciprocal computed redundantly by every lane ahead of the
+// trailing update (one team barrier per column) -> back substitution on warp 0.
+__device__ __forceinline__ void team_sync() { bar_sync(kBarT, kTeam); }
+
+__device__ __forceinline__ void ols_team(EncShared &S, const ChainDesc &d, int tl)
+{
+  const int lane = tl & 31, tw = tl >> 5;
+  const int N = d.n;
+  const int n = d.lenA + d.lenB, n1 = n + 1;
+  const int ld = S.ld;
+  double *cov = S.cov, *W = S.W;
+  const double lambda = d.lambda, nu = d.nu, one_m_lambda = 1.0 - d.lambda;
+  const int ra = tl >> 4, ca = tl & 15;
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;                        // w[lane], w[lane+32], w[lane+64] (every warp its copy)
+  double esum = 0.0;
+  int km = 0;
+  // input windows as doubles: indices [-64, 128) to start with; outside [0, N) reads as 0 (pred.cpp:17-31)
+  for (int q = tl; q < 192; q += kTeam) {
+    const int idx = q - 64;
+    const bool in = idx >= 0 && idx < N;
+    S.xo[idx & (kXW - 1)] = in ? (double)__ldg(d.own + idx) : 0.0;
+    S.xq[idx & (kXW - 1)] = in ? (double)__ldg(d.other + idx) : 0.0;
+  }
+  int fill_end = 128;
+  int t = 0;
+  while (t < N) {
+    if (fill_end < t + 68) {
+      if (tl < 64) {
+        const int idx = fill_end + tl;
+        const bool in = idx < N;
+        S.xo[idx & (kXW - 1)] = in ? (double)__ldg(d.own + idx) : 0.0;
+        S.xq[idx & (kXW - 1)] = in ? (double)__ldg(d.other + idx) : 0.0;
+      }
+      fill_end += 64;
+    }
+    const int kb = min(min(kKB, d.k - km), N - t);
+    team_sync();
+    // ---- regressors of the sub-block: X[u][0..n), X[u][n] = sample ----
+    for (int idx = tl; idx < kb * n1; idx += kTeam) {
+      const int u = idx / n1, j = idx - u * n1;
+      const int tt = t + u;
+      const int sB = max(tt - d.lagB, d.minB) - d.backB;
+      double v;
+      if (j < d.lenA) v = S.xo[(tt - d.lenA + j) & (kXW - 1)];
+      else if (j < n) v = S.xq[(sB + j - d.lenA) & (kXW - 1)];
+      else v = S.xo[tt & (kXW - 1)];
+      S.X[u][j] = v;
+    }
+    team_sync();
+    // ---- predictions: warp u takes sample u; 32 lane-strided fma chains + butterfly (ols.cpp:22-25) ----
+    if (tw < kb) {
+      double acc = 0.0;
+      if (lane < n) acc = __fma_rn(S.X[tw][lane], w0, acc);
+      if (lane + 32 < n) acc = __fma_rn(S.X[tw][lane + 32], w1, acc);
+      if (lane + 64 < n) acc = __fma_rn(S.X[tw][lane + 64], w2, acc);
+      acc = butterfly(acc);
+      if (lane == 0) S.pu[tw] = acc;
+    }
+    team_sync();
+    double pu[kKB];
+#pragma unroll
+    for (int u = 0; u < kKB; u++) pu[u] = u < kb ? S.pu[u] : 0.0;
+    // ---- publish (warp 0) ----
+    if (tw == 0) {
+      if (t + kb > kQ) spin_until_gt(&S.q1_con, t + kb - 1 - kQ);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < kKB; u++) if (u < kb) S.q1[(t + u) & (kQ - 1)] = pu[u];
+        __threadfence_block();
+        st_vol(&S.q1_pub, t + kb);
+      }
+    }
+    // ---- IRLS weights (ols.cpp:29-36): the running sum is serial and cheap, the powers run one per warp ----
+    double es_mine = 1.0;
+#pragma unroll
+    for (int u = 0; u < kKB; u++) {
+      if (u < kb) {
+        const double eo = S.X[u][n] - pu[u];
+        esum = d.beta_sum * esum + fabs(eo);
+        if (tw == u) es_mine = esum;
+      }
+    }
+    if (tw < kb) {
+      const double ff_mine = one_m_lambda * c_pow(es_mine + d.beta_add, -d.beta_pow);
+      if (lane == 0) S.ff[tw] = ff_mine;
+    }
+    team_sync();
+    double ff[kKB];
+#pragma unroll
+    for (int u = 0; u < kKB; u++) ff[u] = u < kb ? S.ff[u] : 0.0;
+    // ---- covariance: kb rank-1 updates per element in one pass (ols.cpp:38-45), 8 x 16 lane grid ----
+    km += kb;
+    const bool solve = km >= d.k;
+    for (int i = ra; i <= n; i += 8) {
+      double xi[kKB];
+#pragma unroll
+      for (int u = 0; u < kKB; u++) xi[u] = u < kb ? S.X[u][i] : 0.0;
+      for (int c = ca; c <= i; c += 32) {
+        double v[2], xc[2][kKB];
+        bool on[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int cc = c + 16 * b;
+          on[b] = cc <= i && !(i == n && cc == n);
+          v[b] = on[b] ? cov[i * ld + cc] : 0.0;
+#pragma unroll
+          for (int u = 0; u < kKB; u++) xc[b][u] = (on[b] && u < kb) ? S.X[u][cc] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+#pragma unroll
+          for (int u = 0; u < kKB; u++)
+            if (u < kb) v[b] = lambda * v[b] + ff[u] * (xi[u] * xc[b][u]);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int cc = c + 16 * b;
+          if (on[b]) {
+            cov[i * ld + cc] = v[b];
+            if (solve) W[i * ld + cc] = (i == cc) ? v[b] + nu : v[b];
+          }
+        }
+      }
+    }
+    if (solve) {
+      km = 0;
+      team_sync();
+      // ---- right-looking LDL^T of (C + nu I), augmented with b as row n. Every lane carries the pivot chain
+      //      (d_j, 1/d_j) redundantly in registers; the owner of element (j+1,j+1) does not store its column-j update
+      //      (it is only ever needed as the next pivot), which leaves a single barrier per column ----
+      bool ok = true;
+      double inv;
+      {
+        const double d0 = W[0];
+        if (d0 < 1e-12) ok = false;
+        inv = 1.0 / d0;
+      }
+      for (int j = 0; j < n && ok; j++) {
+        double inv_next = 0.0;
+        bool ok_next = true;
+        if (j + 1 < n) {
+          const double a = W[(j + 1) * ld + j];
+          const double l = a * inv;
+          const double dn = __fma_rn(-l, a, W[(j + 1) * ld + j + 1]);
+          if (dn < 1e-12) ok_next = false;
+          inv_next = 1.0 / dn;
+        }
+        // trailing update, 2 rows x 2 columns per lane and step: loads, fmas, stores
+        for (int cb = j + 1 + ca; cb < n; cb += 32) {
+          const int c1 = cb + 16;
+          const double cj0 = W[cb * ld + j];
+          const double cj1 = c1 < n ? W[c1 * ld + j] : 0.0;
+          int i0 = j + 1 + ra;
+          if (i0 < cb) i0 += ((cb - i0 + 7) >> 3) << 3;      // rows at or below the tile's first column (c <= i)
+          for (; i0 <= n; i0 += 16) {
+            const int i1 = i0 + 8;
+            const bool r1 = i1 <= n;
+            const double a0 = W[i0 * ld + j], a1 = r1 ? W[i1 * ld + j] : 0.0;
+            const int m0 = min(i0, n - 1), m1 = min(i1, n - 1);
+            const bool s00 = cb <= m0 && !(i0 == j + 1 && cb == j + 1), s01 = c1 <= m0;
+            const bool s10 = r1 && cb <= m1, s11 = r1 && c1 <= m1;
+            double e00 = s00 ? W[i0 * ld + cb] : 0.0, e01 = s01 ? W[i0 * ld + c1] : 0.0;
+            double e10 = s10 ? W[i1 * ld + cb] : 0.0, e11 = s11 ? W[i1 * ld + c1] : 0.0;
+            const double l0 = a0 * inv, l1 = a1 * inv;
+            e00 = __fma_rn(-l0, cj0, e00); e01 = __fma_rn(-l0, cj1, e01);
+            e10 = __fma_rn(-l1, cj0, e10); e11 = __fma_rn(-l1, cj1, e11);
+            if (s00) W[i0 * ld + cb] = e00;
+            if (s01) W[i0 * ld + c1] = e01;
+            if (s10) W[i1 * ld + cb] = e10;
+            if (s11) W[i1 * ld + c1] = e11;
+          }
+        }
+        // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
+        for (int i = j + 1 + tl; i <= n; i += kTeam) W[j * ld + i] = W[i * ld + j] * inv;
+        team_sync();
+        inv = inv_next; ok = ok_next;
+      }
+      if (ok && tw == 0) {
+        // back substitution L^T w = z (z = row n of L), columns in descending order, one fma per element
+        double y0 = lane < n ? W[lane * ld + n] : 0.0;
+        double y1 = lane + 32 < n ? W[(lane + 32) * ld + n] : 0.0;
+        double y2 = lane + 64 < n ? W[(lane + 64) * ld + n] : 0.0;
+        const int lr = min(lane, n - 1);
+        double ln0 = n >= 2 ? W[lr * ld + (n - 1)] : 0.0;     // L[k][lane] for the next step, fetched one step ahead
+        for (int k = n - 1; k >= 1; k--) {
+          const double lk0 = ln0;
+          if (k >= 2) ln0 = W[lr * ld + (k - 1)];
+          const int sl = k >> 5;
+          double yk = sl == 0 ? y0 : (sl == 1 ? y1 : y2);
+          yk = shfl_idx(yk, k & 31);
+          if (lane < k) y0 = __fma_rn(-lk0, yk, y0);
+          if (k > 32 && lane + 32 < k) y1 = __fma_rn(-W[(lane + 32) * ld + k], yk, y1);
+          if (k > 64 && lane + 64 < k) y2 = __fma_rn(-W[(lane + 64) * ld + k], yk, y2);
+        }
+        if (lane < n) S.wv[lane] = y0;
+        if (lane + 32 < n) S.wv[lane + 32] = y1;
+        if (lane + 64 < n) S.wv[lane + 64] = y2;
+      }
+      team_sync();
+      if (ok) {
+        w0 = lane < n ? S.wv[lane] : 0.0;
+        w1 = lane + 32 < n ? S.wv[lane + 32] : 0.0;
+        w2 = lane + 64 < n ? S.wv[lane + 64] : 0.0;
+      }
+    }
+    t += kb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const ChainDesc *__restrict__ descs)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ChainDesc &d = descs[blockIdx.x];
+  EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_ols = d.lenA + d.lenB;
+
+  // ---- carve: shared memory first (histories, OLS matrices, overflow taps), the rest in the chain's HBM scratch ----
+  if (tid == 0) {
+    unsigned int dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    const size_t head = (sizeof(EncShared) + 15) & ~size_t(15);
+    double *sp = reinterpret_cast<double *>(smem_raw + head);
+    long long s_left = ((long long)dyn_bytes - (long long)head) / 8;
+    double *gp = d.scratch;
+    auto take = [&](long long cnt) -> double * {
+      double *r;
+      if (cnt <= s_left) { r = sp; sp += cnt; s_left -= cnt; }
+      else { r = gp; gp += cnt; }
+      return r;
+    };
+    auto take_global = [&](long long cnt) -> double * { double *r = gp; gp += cnt; return r; };
+    const int regs[kStages] = {kR0, kR1, kR2, kR3};
+    for (int s = 0; s < kStages; s++) { S.fpw[s] = take_global(d.vn[s]); S.fmu[s] = take_global(d.vn[s]); }
+    for (int s = kStages - 1; s >= 0; s--) S.h[s] = take(d.vn[s] + 1);
+    const int ld = (n_ols + 1) | 1;
+    S.ld = ld;
+    S.W = take((long long)(n_ols + 1) * ld);
+    S.cov = take((long long)(n_ols + 1) * ld);
+    for (int s = kStages - 1; s >= 0; s--) {
+      const int ov = max(d.vn[s] - kTapThreads * regs[s], 0);
+      S.ow[s] = take(ov); S.opw[s] = take(ov); S.omu[s] = take(ov);
+    }
+  }
+  // zero everything up to the layout block
+  {
+    double *z = reinterpret_cast<double *>(&S);
+    const int nz = (int)(offsetof(EncShared, q1_pub) / 8);
+    for (int i = tid; i < nz; i += kEncThreads) z[i] = 0.0;
+    if (tid == 0) { S.q1_pub = 0; S.q1_con = 0; S.q2_pub = 0; S.q2_con = 0; }
+  }
+  __syncthreads();
+  // ---- tables and initial state ----
+  {
+    const int regs[kStages] = {kR0, kR1, kR2, kR3};
+    for (int s = 0; s < kStages; s++) {
+      const int N = d.vn[s];
+      const double md = d.vmudecay[s], pd = d.vpowdecay[s];
+      double *h = S.h[s], *fpw = S.fpw[s], *fmu = S.fmu[s];
+      double *ow = S.ow[s], *opw = S.opw[s], *omu = S.omu[s];
+      const int r128 = kTapThreads * regs[s];
+      for (int i = tid; i < N; i += kEncThreads) {
+        const double pwv = 1.0 / c_pow((double)(1 + i), pd);  // ls.h:39
+        const double muv = c_pow(md, (double)i);              // ls.h:41
+        fpw[i] = pwv; fmu[i] = muv;
+        h[i] = 0.0;
+        if (i >= r128) { ow[i - r128] = 0.0; opw[i - r128] = pwv; omu[i - r128] = muv; }
+      }
+      if (tid == 0) h[N] = 0.0;
+    }
+    const int ld = S.ld;
+    for (int i = tid; i < (n_ols + 1) * ld; i += kEncThreads) { S.cov[i] = 0.0; S.W[i] = 0.0; }
+  }
+  __syncthreads();
+  if (tid < kStages) {                                       // sum_powtab accumulates sequentially (ls.h:40)
+    const double *fpw = S.fpw[tid];
+    const int N = d.vn[tid];
+    double sp = 0.0;
+    for (int i = 0; i < N; i++) sp += fpw[i];
+    S.sum_pow[tid] = sp;
+  }
+  if (tid < 2 * kMixN) S.v[tid / kMixN][tid % kMixN] = 1.0 / kMixN;        // LSInitType::Uniform (ls.h:199-201)
+  if (tid < 2) S.sw[tid] = 1.0 / 2;                                          // blend.h:22
+  if (tid < d.lm_n) S.rP[tid][tid] = 1.0 / 1.0;                              // rls.cpp:14-15 (nu=1)
+  if (tid < 64) { S.cnt[0][tid] = 4.0; S.cnt[1][tid] = 4.0; S.cnt[2][tid] = 4.0; }   // bias.h:24-28 (freq0=4)
+  __syncthreads();
+
+  // register pool of the CTA (384 x 80): taps 136, scalar warps 56, OLS team 48
+  if (warp < kTapWarps) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    tap_warps(S, d, tid);
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 4) scalar_warp(S, d, lane);
+    else if (warp == 5) bias_warp(S, d, lane);
+    else if (warp == 6) rls_warp(S, d, lane);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    ols_team(S, d, tid - 256);
+  }
+}
+
+} // namespace
+
+size_t predictor_enc_shared_bytes() { return (sizeof(EncShared) + 15) & ~size_t(15); }
+
+// doubles of HBM scratch a chain may need when nothing but the fixed block fits shared memory
+long long predictor_enc_scratch_doubles(const int *vn, int n_ols)
+{
+  long long t = 0;
+  for (int s = 0; s < kStages; s++) t += 6LL * vn[s] + 1;
+  const long long ld = (n_ols + 1) | 1;
+  t += 2LL * (n_ols + 1) * ld;
+  return t + 16;
+}
+
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream)
+{
+  static int attr_smem = 0;
+  if (attr_smem < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(predictor_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem_bytes;
+  }
+  predictor_enc_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs);
+  return cudaGetLastError();
+}
+
+} // namespace sacb
