@@ -40,6 +40,8 @@ struct ChainDesc {
   // --- spill space in HBM for arrays that do not fit the CTA's shared memory ---
   double *scratch;
   long long scratch_doubles;
+  double *scratch_ols;      // encode direction: OLS matrices that do not fit the OLS kernel's shared memory
+  double *plpc;             // encode direction: OLS predictions p_lpc[n], written by ols_kernel, read by cascade_kernel
   // --- outputs ---
   long long *l1sum;         // sum |e|
   long long *sqsum;         // sum e*e

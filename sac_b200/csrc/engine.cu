@@ -129,6 +129,7 @@ int Engine::init(int dev)
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
+  if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
   SACB_CUDA(bt.init(stream));
   return SAC_OK;
 }
@@ -136,7 +137,7 @@ void Engine::destroy()
 {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
-  d_descs.release(); h_descs.release(); d_scratch.release(); d_resid.release(); d_sums.release(); d_flags.release();
+  d_descs.release(); h_descs.release(); d_scratch.release(); d_scratch_ols.release(); d_plpc.release(); d_resid.release(); d_sums.release(); d_flags.release();
   h_sums.release(); h_flags.release(); d_bpjobs.release(); h_bpjobs.release(); d_csig0.release(); d_hist.release();
   d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release();
   bt.destroy();
@@ -173,6 +174,12 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     for (int cc = 0; cc < j.win->nch; cc++, c++) soff[c + 1] = soff[c] + ((chain_scratch_doubles(hps[ji], cc, j.win->nch) + 1) & ~1LL);
   }
   SACB_CUDA(d_scratch.reserve((size_t)soff[nchains]));
+  std::vector<long long> ooff(nchains + 1, 0);
+  c = 0;
+  for (size_t ji = 0; ji < jobs.size(); ji++)
+    for (int cc = 0; cc < jobs[ji].win->nch; cc++, c++) ooff[c + 1] = ooff[c] + ((predictor_ols_scratch_doubles(ols_order(hps[ji], cc)) + 1) & ~1LL);
+  SACB_CUDA(d_scratch_ols.reserve((size_t)ooff[nchains]));
+  SACB_CUDA(d_plpc.reserve(stride * nchains));
   c = 0;
   for (size_t ji = 0; ji < jobs.size(); ji++) {
     const Job &j = jobs[ji];
@@ -182,15 +189,17 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
       d.resid = d_resid.p + (size_t)c * stride;
       d.scratch = d_scratch.p + soff[c];
       d.scratch_doubles = soff[c + 1] - soff[c];
+      d.scratch_ols = d_scratch_ols.p + ooff[c];
+      d.plpc = d_plpc.p + (size_t)c * stride;
       d.l1sum = d_sums.p + c; d.sqsum = d_sums.p + nchains + c; d.flags = d_flags.p + c;
       chain_job.push_back((int)ji); chain_ch.push_back(actual);
     }
   }
   SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, stream));
+  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, ols_smem_bytes, stream));
   SACB_CUDA(cudaEventRecord(ev[1], stream));
-  launches++; last_launches[0]++;
+  launches += 2; last_launches[0] += 2;                             // ols_kernel + cascade_kernel
   return SAC_OK;
 }
 

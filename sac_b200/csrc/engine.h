@@ -70,7 +70,8 @@ struct Engine {           // sac_engine
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   BitplaneTables bt;
   int smem_bytes = 72 * 1024;        // decode-direction kernel (predictor.cu)
-  int enc_smem_bytes = 100 * 1024;   // encode-direction kernel (predictor_enc.cu): 2 CTAs per SM
+  int enc_smem_bytes = 100 * 1024;   // cascade kernel (predictor_enc.cu): 2 CTAs per SM
+  int ols_smem_bytes = 36 * 1024;    // OLS kernel: 6 CTAs per SM; matrices up to n = 32 stay in shared memory
   long long launches = 0;
   double last_ms[3] = {0, 0, 0};
   long long last_launches[3] = {0, 0, 0};
@@ -78,6 +79,8 @@ struct Engine {           // sac_engine
   DevBuf<ChainDesc> d_descs;
   PinBuf<ChainDesc> h_descs;
   DevBuf<double> d_scratch;
+  DevBuf<double> d_scratch_ols;
+  DevBuf<double> d_plpc;          // OLS predictions per chain (encode direction)
   DevBuf<int32_t> d_resid;
   DevBuf<long long> d_sums;       // per chain: l1, sq, nbytes
   DevBuf<int> d_flags;            // per chain: flags, maxbpn
@@ -104,8 +107,9 @@ struct Engine {           // sac_engine
 
 // kernels (predictor.cu, cost.cu)
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream);
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols);
+long long predictor_ols_scratch_doubles(int n_ols);
 size_t predictor_enc_shared_bytes();
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream);

@@ -1,29 +1,28 @@
-// predictor_enc.cu -- encode-direction predictor as a pipeline of specialised warps (sm_100a).
+// predictor_enc.cu -- encode-direction predictor as two kernels of specialised warps (sm_100a).
 //
 // In the encoder the per-sample recurrence of one chain (OLS -> NLMS cascade + RLS -> mix -> bias, the reference's
-// Predictor for one coded channel, /root/reference src/libsac/pred.cpp:4-45) falls apart into three feed-forward
+// Predictor for one coded channel, /root/reference src/libsac/pred.cpp:4-45) falls apart into feed-forward
 // recurrences, because every stage is driven by *input* samples (teacher forcing):
 //
 //   OLS  (ols.cpp)                  p_lpc(t)            depends on inputs only
 //   cascade (cascade.h, ls.h, rls)  p_lms(t)            depends on inputs and p_lpc
 //   bias (bias.h) + residual        e(t)                depends on inputs and p_lpc + p_lms
 //
-// One CTA (256 threads) runs one chain; its eight warps are
-//
-//   warps 0-3  tap warps   128 lane-strided NLMS taps x 4 stages. Weights, power table and mu table of the first
-//                          kR0/kR1/kR2/kR3 x 128 taps of each stage live in REGISTERS (setmaxnreg.inc 176), the
-//                          history ring in shared memory; longer stages continue from shared memory / HBM scratch.
-//   warp 4     S  cascade scalars: stage predictions, 2-expert mix, stage targets, NLMS gradients, mix update
-//   warp 5     O  OLS: regressors, k predictions per block from a register-resident w, IRLS weights, covariance
-//                 update (k rank-1 updates applied per element in one pass), look-ahead LDL^T, back substitution
-//   warp 6     B  bias stage, rounding, residual, cost sums
-//   warp 7     R  RLS stage (5th cascade stage)
-//
-// O -> S and S -> B are rings in shared memory (depth 32) so that O runs ahead by a whole solve block and B trails;
-// taps <-> S and S <-> R meet at named barriers (bar.arrive / bar.sync) twice per sample.
+// ols_kernel      one CTA of 4 warps per chain (light: several CTAs per SM). A block of k samples: regressors (all
+//                 lanes) -> one prediction per warp -> IRLS weights (one power per warp) -> covariance, k rank-1
+//                 updates per element in one pass -> right-looking LDL^T with the next pivot and its reciprocal
+//                 computed ahead of the trailing update -> back substitution. p_lpc(t) goes to HBM (8 B per sample).
+// cascade_kernel  one CTA of 8 warps per chain, two warpgroups with their own register budgets (setmaxnreg):
+//   warps 0-3   tap warps  128 lane-strided NLMS taps x 4 stages. Weights, power table and mu table of the first
+//                          kR0/kR1/kR2/kR3 x 128 taps of each stage live in REGISTERS, the history ring in shared
+//                          memory; longer stages continue from shared memory / HBM scratch.
+//   warp 4      S  cascade scalars: stage predictions, 2-expert mix, stage targets, NLMS gradients, mix update
+//   warp 5      B  bias stage, rounding, residual, cost sums (trails S through a ring in shared memory)
+//   warp 6      R  RLS stage (5th cascade stage)
+//   taps <-> S and S <-> R meet at named barriers (bar.arrive / bar.sync) twice per sample.
 //
 // The arithmetic is the canonical order of DESIGN.md section 2 (identical to predictor.cu, which remains the
-// decode-direction kernel): results are bit-identical to oracle/sac_oracle.cpp in SACO_ORDER_B200 / SACO_MATH_CANON.
+// decode-direction kernel); the -m gpu tests compare residuals bit for bit with the CPU restatement of that order.
 // Reference behaviour restated: src/libsac/pred.cpp:4-45, src/pred/{ols.cpp,ls.h,cascade.h,blend.h,rls.cpp,rls.h,
 // bias.h}, src/common/math.h:14-78, src/libsac/libsac.cpp:94-142.
 #include "chain.h"
@@ -41,9 +40,9 @@ using sac_canon::c_round;
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kEncThreads = 384;                        // 3 warpgroups: taps | S, B, R | OLS team
-constexpr int kTeam = 128;
-constexpr int kR0 = 10, kR1 = 2, kR2 = 1, kR3 = 1;   // register-resident tap slots per thread and stage
+constexpr int kEncThreads = 256;                        // cascade kernel: 2 warpgroups: taps | S, B, R
+constexpr int kTeam = 128;                              // OLS kernel: one team of 4 warps
+constexpr int kR0 = 12, kR1 = 4, kR2 = 2, kR3 = 1;   // register-resident tap slots per thread and stage
 constexpr int kQ = 32;                                // ring depth (samples)
 constexpr int kXW = 256;                              // input window (samples, power of two)
 constexpr int kXS = 100;                              // row stride of the regressor block
@@ -115,27 +114,32 @@ struct EncShared {
   double hist_in[8], hist_d[8], mixw[4][3];
   double cnt[3][64], cval[3][64];
   double bmean, bvar;
-  // O: regressor block and input windows
-  double X[kKB][kXS];
-  double xo[kXW], xq[kXW];
-  double pu[kKB], ff[kKB], wv[kMaxOls];
-  // rings
-  double q1[kQ], q2[kQ];
-  int q1_pub, q1_con, q2_pub, q2_con;
+  // S -> B ring
+  double q2[kQ];
+  int q2_pub, q2_con;
   // layout
   double *h[kStages], *ow[kStages], *opw[kStages], *omu[kStages];
   double *fpw[kStages], *fmu[kStages];   // full tables (HBM scratch), used at start-up only
   double sum_pow[kStages];
-  double *cov, *W;
-  int ld;
 };
 
+struct OlsShared {
+  double X[kKB][kXS];                    // regressor block
+  double xo[kXW], xq[kXW];               // input windows as doubles
+  double pu[kKB], ff[kKB], wv[kMaxOls];
+  double *cov, *W;
+  int ld;
+  int w_shared;                          // work matrix lies in shared memory (fast LDL path)
+};
+
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 __device__ __forceinline__ double ldd_vol(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
 __device__ __forceinline__ void spin_until_gt(const int *ctr, int v)
 {
-  while (ld_vol(ctr) <= v) __nanosleep(20);
+  while (ld_vol(ctr) <= v) __nanosleep(40);
   __threadfence_block();                                     // acquire: ring data is read after the counter
 }
 
@@ -268,11 +272,18 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
   const double my_sp = lane < kStages ? S.sum_pow[lane] : 0.0;
   int pos = 0;
   bool bad = false;
+  const double *plpc = d.plpc;
   int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
   int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
+  double lcur = lane < n ? __ldg(plpc + lane) : 0.0;
+  double lnext = 32 + lane < n ? __ldg(plpc + 32 + lane) : 0.0;
   for (int t = 0; t < n; t++) {
-    if ((t & 31) == 0 && t) { vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0; }
+    if ((t & 31) == 0 && t) {
+      vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0;
+      lcur = lnext; lnext = t + 32 + lane < n ? __ldg(plpc + t + 32 + lane) : 0.0;
+    }
     const double val = (double)__shfl_sync(kFull, vcur, t & 31);
+    const double p_lpc = shfl_idx(lcur, t & 31);
     // state that does not depend on this sample's predictions
     const double sw0 = S.sw[0], sw1 = S.sw[1];
     double v0[kMixN], v1[kMixN], wi[kMixN];
@@ -281,10 +292,6 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
       v0[i] = S.v[0][i]; v1[i] = S.v[1][i];
       wi[i] = dmax(0.0 + ((0.0 + v0[i] * sw0) + v1[i] * sw1), 0.0);
     }
-    spin_until_gt(&S.q1_pub, t);
-    const double p_lpc = ldd_vol(&S.q1[t & (kQ - 1)]);
-    __syncwarp();
-    if (lane == 0) st_vol(&S.q1_con, t + 1);
     const double target = val - p_lpc;
     if (t) bar_sync(kBarB4, 64);                             // p_rls for this sample
     bar_sync(kBarB1, 160);                                   // tap partial sums
@@ -505,7 +512,7 @@ __device__ __forceinline__ void bias_warp(EncShared &S, const ChainDesc &d, int 
 // trailing update (one team barrier per column) -> back substitution on warp 0.
 __device__ __forceinline__ void team_sync() { bar_sync(kBarT, kTeam); }
 
-__device__ __forceinline__ void ols_team(EncShared &S, const ChainDesc &d, int tl)
+__device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int tl)
 {
   const int lane = tl & 31, tw = tl >> 5;
   const int N = d.n;
@@ -563,16 +570,8 @@ __device__ __forceinline__ void ols_team(EncShared &S, const ChainDesc &d, int t
     double pu[kKB];
 #pragma unroll
     for (int u = 0; u < kKB; u++) pu[u] = u < kb ? S.pu[u] : 0.0;
-    // ---- publish (warp 0) ----
-    if (tw == 0) {
-      if (t + kb > kQ) spin_until_gt(&S.q1_con, t + kb - 1 - kQ);
-      if (lane == 0) {
-#pragma unroll
-        for (int u = 0; u < kKB; u++) if (u < kb) S.q1[(t + u) & (kQ - 1)] = pu[u];
-        __threadfence_block();
-        st_vol(&S.q1_pub, t + kb);
-      }
-    }
+    // ---- predictions to HBM ----
+    if (tl < kb) d.plpc[t + tl] = S.pu[tl];
     // ---- IRLS weights (ols.cpp:29-36): the running sum is serial and cheap, the powers run one per warp ----
     double es_mine = 1.0;
 #pragma unroll
@@ -638,45 +637,108 @@ __device__ __forceinline__ void ols_team(EncShared &S, const ChainDesc &d, int t
         if (d0 < 1e-12) ok = false;
         inv = 1.0 / d0;
       }
-      for (int j = 0; j < n && ok; j++) {
-        double inv_next = 0.0;
-        bool ok_next = true;
-        if (j + 1 < n) {
-          const double a = W[(j + 1) * ld + j];
-          const double l = a * inv;
-          const double dn = __fma_rn(-l, a, W[(j + 1) * ld + j + 1]);
-          if (dn < 1e-12) ok_next = false;
-          inv_next = 1.0 / dn;
-        }
-        // trailing update, 2 rows x 2 columns per lane and step: loads, fmas, stores
-        for (int cb = j + 1 + ca; cb < n; cb += 32) {
-          const int c1 = cb + 16;
-          const double cj0 = W[cb * ld + j];
-          const double cj1 = c1 < n ? W[c1 * ld + j] : 0.0;
-          int i0 = j + 1 + ra;
-          if (i0 < cb) i0 += ((cb - i0 + 7) >> 3) << 3;      // rows at or below the tile's first column (c <= i)
-          for (; i0 <= n; i0 += 16) {
-            const int i1 = i0 + 8;
-            const bool r1 = i1 <= n;
-            const double a0 = W[i0 * ld + j], a1 = r1 ? W[i1 * ld + j] : 0.0;
-            const int m0 = min(i0, n - 1), m1 = min(i1, n - 1);
-            const bool s00 = cb <= m0 && !(i0 == j + 1 && cb == j + 1), s01 = c1 <= m0;
-            const bool s10 = r1 && cb <= m1, s11 = r1 && c1 <= m1;
-            double e00 = s00 ? W[i0 * ld + cb] : 0.0, e01 = s01 ? W[i0 * ld + c1] : 0.0;
-            double e10 = s10 ? W[i1 * ld + cb] : 0.0, e11 = s11 ? W[i1 * ld + c1] : 0.0;
-            const double l0 = a0 * inv, l1 = a1 * inv;
-            e00 = __fma_rn(-l0, cj0, e00); e01 = __fma_rn(-l0, cj1, e01);
-            e10 = __fma_rn(-l1, cj0, e10); e11 = __fma_rn(-l1, cj1, e11);
-            if (s00) W[i0 * ld + cb] = e00;
-            if (s01) W[i0 * ld + c1] = e01;
-            if (s10) W[i1 * ld + cb] = e10;
-            if (s11) W[i1 * ld + c1] = e11;
+      if (S.w_shared) {
+        // Fast path, work matrix in shared memory. Relative to the pivot (j,j) the element offsets of a lane never
+        // change, so a column step is a fixed 4-row x 2-column pattern per lane and 32 x 32 block: all loads are issued
+        // first (32-bit shared addresses), then the fmas, then the stores.
+        const uint32_t ldb = (uint32_t)ld * 8u;
+        uint32_t pjj = (uint32_t)__cvta_generic_to_shared(W);
+        const uint32_t r0 = (uint32_t)(1 + ra) * ldb, rstep = 8u * ldb;
+        const uint32_t q0 = (uint32_t)(1 + ca) * 8u;
+        for (int j = 0; j < n && ok; j++) {
+          const int m = n - j;                                     // trailing rows rel 1..m, trailing columns rel 1..m-1
+          double inv_next = 0.0;
+          bool ok_next = true;
+          if (m > 1) {
+            const double a = lds_f64(pjj + ldb);
+            const double dd = lds_f64(pjj + ldb + 8u);
+            const double l = a * inv;
+            const double dn = __fma_rn(-l, a, dd);
+            if (dn < 1e-12) ok_next = false;
+            inv_next = 1.0 / dn;
           }
+          for (int rb = 0; rb < m; rb += 32) {
+            for (int cb = 0; cb <= rb && cb < m - 1; cb += 32) {
+              const uint32_t rbase = pjj + (uint32_t)rb * ldb + r0;
+              const uint32_t cbase = (uint32_t)cb * 8u + q0;
+              bool rv[4], cv[2];
+              double al[4], cj[2], e[4][2];
+#pragma unroll
+              for (int a = 0; a < 4; a++) { rv[a] = rb + 1 + ra + 8 * a <= m; al[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep) : 0.0; }
+#pragma unroll
+              for (int b = 0; b < 2; b++) {
+                cv[b] = cb + 1 + ca + 16 * b <= m - 1;
+                cj[b] = cv[b] ? lds_f64(pjj + (uint32_t)(cb + 1 + ca + 16 * b) * ldb) : 0.0;
+              }
+              bool on[4][2];
+#pragma unroll
+              for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                  const int rr = rb + 1 + ra + 8 * a, qq = cb + 1 + ca + 16 * b;
+                  on[a][b] = rv[a] && cv[b] && qq <= rr && !(rr == 1 && qq == 1);
+                  e[a][b] = on[a][b] ? lds_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u) : 0.0;
+                }
+#pragma unroll
+              for (int a = 0; a < 4; a++) {
+                const double la = al[a] * inv;
+#pragma unroll
+                for (int b = 0; b < 2; b++) e[a][b] = __fma_rn(-la, cj[b], e[a][b]);
+              }
+#pragma unroll
+              for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+                  if (on[a][b]) sts_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u, e[a][b]);
+            }
+          }
+          // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
+          for (int r = 1 + tl; r <= m; r += kTeam) sts_f64(pjj + (uint32_t)r * 8u, lds_f64(pjj + (uint32_t)r * ldb) * inv);
+          team_sync();
+          pjj += ldb + 8u;
+          inv = inv_next; ok = ok_next;
         }
-        // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
-        for (int i = j + 1 + tl; i <= n; i += kTeam) W[j * ld + i] = W[i * ld + j] * inv;
-        team_sync();
-        inv = inv_next; ok = ok_next;
+      } else {
+        for (int j = 0; j < n && ok; j++) {
+          double inv_next = 0.0;
+          bool ok_next = true;
+          if (j + 1 < n) {
+            const double a = W[(j + 1) * ld + j];
+            const double l = a * inv;
+            const double dn = __fma_rn(-l, a, W[(j + 1) * ld + j + 1]);
+            if (dn < 1e-12) ok_next = false;
+            inv_next = 1.0 / dn;
+          }
+          // trailing update, 2 rows x 2 columns per lane and step: loads, fmas, stores
+          for (int cb = j + 1 + ca; cb < n; cb += 32) {
+            const int c1 = cb + 16;
+            const double cj0 = W[cb * ld + j];
+            const double cj1 = c1 < n ? W[c1 * ld + j] : 0.0;
+            int i0 = j + 1 + ra;
+            if (i0 < cb) i0 += ((cb - i0 + 7) >> 3) << 3;      // rows at or below the tile's first column (c <= i)
+            for (; i0 <= n; i0 += 16) {
+              const int i1 = i0 + 8;
+              const bool r1 = i1 <= n;
+              const double a0 = W[i0 * ld + j], a1 = r1 ? W[i1 * ld + j] : 0.0;
+              const int m0 = min(i0, n - 1), m1 = min(i1, n - 1);
+              const bool s00 = cb <= m0 && !(i0 == j + 1 && cb == j + 1), s01 = c1 <= m0;
+              const bool s10 = r1 && cb <= m1, s11 = r1 && c1 <= m1;
+              double e00 = s00 ? W[i0 * ld + cb] : 0.0, e01 = s01 ? W[i0 * ld + c1] : 0.0;
+              double e10 = s10 ? W[i1 * ld + cb] : 0.0, e11 = s11 ? W[i1 * ld + c1] : 0.0;
+              const double l0 = a0 * inv, l1 = a1 * inv;
+              e00 = __fma_rn(-l0, cj0, e00); e01 = __fma_rn(-l0, cj1, e01);
+              e10 = __fma_rn(-l1, cj0, e10); e11 = __fma_rn(-l1, cj1, e11);
+              if (s00) W[i0 * ld + cb] = e00;
+              if (s01) W[i0 * ld + c1] = e01;
+              if (s10) W[i1 * ld + cb] = e10;
+              if (s11) W[i1 * ld + c1] = e11;
+            }
+          }
+          // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
+          for (int i = j + 1 + tl; i <= n; i += kTeam) W[j * ld + i] = W[i * ld + j] * inv;
+          team_sync();
+          inv = inv_next; ok = ok_next;
+        }
       }
       if (ok && tw == 0) {
         // back substitution L^T w = z (z = row n of L), columns in descending order, one fma per element
@@ -711,15 +773,42 @@ __device__ __forceinline__ void ols_team(EncShared &S, const ChainDesc &d, int t
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const ChainDesc *__restrict__ descs)
+__global__ void __launch_bounds__(kTeam, 6) ols_kernel(const ChainDesc *__restrict__ descs)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ChainDesc &d = descs[blockIdx.x];
+  OlsShared &S = *reinterpret_cast<OlsShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int n_ols = d.lenA + d.lenB;
+  const int ld = (n_ols + 1) | 1;
+  if (tid == 0) {
+    unsigned int dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    const size_t head = (sizeof(OlsShared) + 15) & ~size_t(15);
+    double *sp = reinterpret_cast<double *>(smem_raw + head);
+    long long s_left = ((long long)dyn_bytes - (long long)head) / 8;
+    double *gp = d.scratch_ols;
+    const long long cnt = (long long)(n_ols + 1) * ld;
+    S.ld = ld;
+    S.w_shared = cnt <= s_left;
+    if (cnt <= s_left) { S.W = sp; sp += cnt; s_left -= cnt; } else { S.W = gp; gp += cnt; }
+    if (cnt <= s_left) { S.cov = sp; sp += cnt; s_left -= cnt; } else { S.cov = gp; gp += cnt; }
+  }
+  __syncthreads();
+  for (int i = tid; i < (n_ols + 1) * ld; i += kTeam) { S.cov[i] = 0.0; S.W[i] = 0.0; }
+  for (int i = tid; i < kMaxOls; i += kTeam) S.wv[i] = 0.0;
+  __syncthreads();
+  ols_team(S, d, tid);
+}
+
+__global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc *__restrict__ descs)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ChainDesc &d = descs[blockIdx.x];
   EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_ols = d.lenA + d.lenB;
 
-  // ---- carve: shared memory first (histories, OLS matrices, overflow taps), the rest in the chain's HBM scratch ----
+  // ---- carve: shared memory first (histories, overflow taps), the rest in the chain's HBM scratch ----
   if (tid == 0) {
     unsigned int dyn_bytes;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
@@ -737,10 +826,6 @@ __global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const Cha
     const int regs[kStages] = {kR0, kR1, kR2, kR3};
     for (int s = 0; s < kStages; s++) { S.fpw[s] = take_global(d.vn[s]); S.fmu[s] = take_global(d.vn[s]); }
     for (int s = kStages - 1; s >= 0; s--) S.h[s] = take(d.vn[s] + 1);
-    const int ld = (n_ols + 1) | 1;
-    S.ld = ld;
-    S.W = take((long long)(n_ols + 1) * ld);
-    S.cov = take((long long)(n_ols + 1) * ld);
     for (int s = kStages - 1; s >= 0; s--) {
       const int ov = max(d.vn[s] - kTapThreads * regs[s], 0);
       S.ow[s] = take(ov); S.opw[s] = take(ov); S.omu[s] = take(ov);
@@ -749,9 +834,9 @@ __global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const Cha
   // zero everything up to the layout block
   {
     double *z = reinterpret_cast<double *>(&S);
-    const int nz = (int)(offsetof(EncShared, q1_pub) / 8);
+    const int nz = (int)(offsetof(EncShared, q2_pub) / 8);
     for (int i = tid; i < nz; i += kEncThreads) z[i] = 0.0;
-    if (tid == 0) { S.q1_pub = 0; S.q1_con = 0; S.q2_pub = 0; S.q2_con = 0; }
+    if (tid == 0) { S.q2_pub = 0; S.q2_con = 0; }
   }
   __syncthreads();
   // ---- tables and initial state ----
@@ -772,8 +857,6 @@ __global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const Cha
       }
       if (tid == 0) h[N] = 0.0;
     }
-    const int ld = S.ld;
-    for (int i = tid; i < (n_ols + 1) * ld; i += kEncThreads) { S.cov[i] = 0.0; S.W[i] = 0.0; }
   }
   __syncthreads();
   if (tid < kStages) {                                       // sum_powtab accumulates sequentially (ls.h:40)
@@ -789,18 +872,15 @@ __global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const Cha
   if (tid < 64) { S.cnt[0][tid] = 4.0; S.cnt[1][tid] = 4.0; S.cnt[2][tid] = 4.0; }   // bias.h:24-28 (freq0=4)
   __syncthreads();
 
-  // register pool of the CTA (384 x 80): taps 136, scalar warps 56, OLS team 48
+  // register pool of the CTA (256 x 128): taps 176, scalar warps 80
   if (warp < kTapWarps) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     tap_warps(S, d, tid);
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == 4) scalar_warp(S, d, lane);
     else if (warp == 5) bias_warp(S, d, lane);
     else if (warp == 6) rls_warp(S, d, lane);
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-    ols_team(S, d, tid - 256);
   }
 }
 
@@ -808,25 +888,37 @@ __global__ void __launch_bounds__(kEncThreads, 2) predictor_enc_kernel(const Cha
 
 size_t predictor_enc_shared_bytes() { return (sizeof(EncShared) + 15) & ~size_t(15); }
 
-// doubles of HBM scratch a chain may need when nothing but the fixed block fits shared memory
+// doubles of HBM scratch a chain may need when nothing but the fixed blocks fit shared memory
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols)
 {
   long long t = 0;
   for (int s = 0; s < kStages; s++) t += 6LL * vn[s] + 1;
-  const long long ld = (n_ols + 1) | 1;
-  t += 2LL * (n_ols + 1) * ld;
   return t + 16;
 }
-
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream)
+long long predictor_ols_scratch_doubles(int n_ols)
 {
-  static int attr_smem = 0;
+  const long long ld = (n_ols + 1) | 1;
+  return 2LL * (n_ols + 1) * ld + 16;
+}
+
+// residuals of every chain: OLS predictions first (ols_kernel -> ChainDesc::plpc), then the cascade
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream)
+{
+  static int attr_smem = 0, attr_ols = 0;
   if (attr_smem < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(predictor_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     attr_smem = smem_bytes;
   }
-  predictor_enc_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs);
+  if (attr_ols < ols_smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ols_smem_bytes);
+    if (e != cudaSuccess) return e;
+    attr_ols = ols_smem_bytes;
+  }
+  ols_kernel<<<nchains, kTeam, ols_smem_bytes, stream>>>(d_descs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs);
   return cudaGetLastError();
 }
 
