@@ -315,6 +315,77 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
     w.win = reinterpret_cast<Window *>(sac_window_create(reinterpret_cast<sac_engine *>(e), nch, pp, w.n, w.mm));
     if (!w.win) return SAC_E_CUDA;
   }
+  // ---- final pass (k=1, whole frame) + payload emission of one frame on a helper engine: it is launched as soon as
+  //      the frame's profile is known and runs on its own high-priority stream while the main stream searches the
+  //      next frame; results are collected at the end (WriteEncoded order) ----
+  struct Final { Engine *eng = nullptr; bool launched = false; int nchains = 0; std::vector<int> cj, cc; std::vector<size_t> boff; };
+  std::vector<Final> fin(nframes);
+  const int kHelpers = 4;
+  auto collect_final = [&](int f) -> int {
+    Final &F = fin[f];
+    if (!F.launched || !F.eng) return SAC_OK;
+    Engine *h = F.eng;
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < F.nchains; c++)
+      if (h->h_flags.p[c]) { set_error("final pass: predictor state became non-finite"); return SAC_E_UNSUPPORTED; }
+    // serialise (WriteEncoded / WriteBlockHeader / EncodeProfile, libsac.cpp:507-578)
+    std::vector<uint8_t> payload;
+    push32(out, (uint32_t)fw[f].n);
+    for (int i = 0; i < kProfileSize; i++) { uint32_t ix; std::memcpy(&ix, &fw[f].profile[i], 4); push32(out, ix); }
+    for (int ch = 0; ch < nch; ch++) {
+      int c = -1;
+      for (int q = 0; q < F.nchains; q++) if (F.cc[q] == ch) c = q;
+      const long long nb = h->h_sums.p[2 * F.nchains + c];
+      const int maxbpn = h->h_flags.p[F.nchains + c];
+      payload.resize((size_t)nb);
+      SACB_CUDA(cudaMemcpyAsync(payload.data(), h->d_bytes.p + F.boff[c], (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+      SACB_CUDA(cudaStreamSynchronize(h->stream));
+      push32(out, (uint32_t)nb); push32(out, (uint32_t)fw[f].mean[ch]); push32(out, (uint32_t)fw[f].mm[2 * ch]); push32(out, (uint32_t)fw[f].mm[2 * ch + 1]);
+      push16(out, (uint16_t)(maxbpn & 0xff));
+      out.insert(out.end(), payload.begin(), payload.end());
+    }
+    F.eng = nullptr;
+    return SAC_OK;
+  };
+  auto launch_final = [&](int f) -> int {
+    Final &F = fin[f];
+    // a helper is reused only after the frame that used it has been collected; frames are collected in order
+    if (f >= kHelpers) { for (int g = 0; g <= f - kHelpers; g++) { int rc = collect_final(g); if (rc) return rc; } }
+    Engine *h = e->helper(f % kHelpers);
+    if (!h) return SAC_E_CUDA;
+    F.eng = h;
+    std::vector<Job> jobs(1);
+    jobs[0].win = fw[f].win; jobs[0].from = 0; jobs[0].n = fw[f].n; jobs[0].k = 1;
+    std::memcpy(jobs[0].profile, fw[f].profile, sizeof(float) * kProfileSize);
+    h->begin_call();
+    size_t stride;
+    int rc = h->run_predict(jobs, F.cj, F.cc, stride);
+    if (rc) return rc;
+    const int nchains = F.nchains = (int)F.cj.size();
+    SACB_CUDA(h->h_bpjobs.reserve(nchains));
+    SACB_CUDA(h->d_bpjobs.reserve(nchains));
+    SACB_CUDA(h->d_csig0.reserve((size_t)65536 * nchains));
+    F.boff.assign(nchains + 1, 0);
+    for (int c = 0; c < nchains; c++) F.boff[c + 1] = F.boff[c] + (((size_t)fw[f].n * 4 + 1024 + 15) & ~size_t(15));
+    SACB_CUDA(h->d_bytes.reserve(F.boff[nchains]));
+    for (int c = 0; c < nchains; c++) {
+      BpJob &b = h->h_bpjobs.p[c];
+      std::memset(&b, 0, sizeof(b));
+      b.buf = h->d_resid.p + (size_t)c * stride; b.n = fw[f].n; b.signed_input = 1; b.maxbpn = -1;
+      b.csig0 = h->d_csig0.p + (size_t)65536 * c; b.out = h->d_bytes.p + F.boff[c];
+      b.nbytes = h->d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = h->d_flags.p + nchains + c;
+    }
+    SACB_CUDA(cudaMemcpyAsync(h->d_bpjobs.p, h->h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(launch_bitplane(h->bt, h->d_bpjobs.p, nchains, 1, h->stream));
+    h->launches++; h->last_launches[1]++;
+    SACB_CUDA(h->h_sums.reserve((size_t)3 * nchains));
+    SACB_CUDA(h->h_flags.reserve((size_t)2 * nchains));
+    SACB_CUDA(cudaMemcpyAsync(h->h_sums.p, h->d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(h->h_flags.p, h->d_flags.p, sizeof(int) * 2 * nchains, cudaMemcpyDeviceToHost, h->stream));
+    F.launched = true;
+    return SAC_OK;
+  };
+
   // ---- search (FrameCoder::Optimize, libsac.cpp:365-427; Predict :461-476) ----
   std::vector<int> dims;
   for (int i = 0; i < kProfileSize; i++) if (i != 56 && i != 57) dims.push_back(i);
@@ -373,6 +444,8 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
         const auto &xb = ss[f - f0]->best_x();
         for (int i = 0; i < D; i++) fw[f].profile[dims[i]] = (float)xb[i];                // libsac.cpp:418-420
         std::memcpy(cur, fw[f].profile, sizeof(cur));
+        int rc = launch_final(f);                                    // overlaps the next group's search
+        if (rc) return rc;
       }
     }
   } else {
@@ -380,61 +453,10 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
   }
   std::memcpy(profile_io, cur, sizeof(cur));
 
-  // ---- final pass (k=1, whole frame) for all frames in one batch, then payload emission ----
-  std::vector<Job> jobs(nframes);
-  for (int f = 0; f < nframes; f++) {
-    jobs[f].win = fw[f].win; jobs[f].from = 0; jobs[f].n = fw[f].n; jobs[f].k = 1;
-    std::memcpy(jobs[f].profile, fw[f].profile, sizeof(cur));
-  }
-  e->begin_call();
-  std::vector<int> cj, cc;
-  size_t stride;
-  int rc = e->run_predict(jobs, cj, cc, stride);
-  if (rc) return rc;
-  const int nchains = (int)cj.size();
-  SACB_CUDA(e->h_bpjobs.reserve(nchains));
-  SACB_CUDA(e->d_bpjobs.reserve(nchains));
-  SACB_CUDA(e->d_csig0.reserve((size_t)65536 * nchains));
-  std::vector<size_t> boff(nchains + 1, 0);
-  for (int c = 0; c < nchains; c++) boff[c + 1] = boff[c] + (((size_t)jobs[cj[c]].n * 4 + 1024 + 15) & ~size_t(15));
-  SACB_CUDA(e->d_bytes.reserve(boff[nchains]));
-  for (int c = 0; c < nchains; c++) {
-    BpJob &b = e->h_bpjobs.p[c];
-    std::memset(&b, 0, sizeof(b));
-    b.buf = e->d_resid.p + (size_t)c * stride; b.n = jobs[cj[c]].n; b.signed_input = 1; b.maxbpn = -1;
-    b.csig0 = e->d_csig0.p + (size_t)65536 * c; b.out = e->d_bytes.p + boff[c];
-    b.nbytes = e->d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = e->d_flags.p + nchains + c;
-  }
-  SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, e->stream));
-  SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
-  SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, nchains, 1, e->stream));
-  SACB_CUDA(cudaEventRecord(e->ev[3], e->stream));
-  e->launches++; e->last_launches[1]++;
-  SACB_CUDA(e->h_sums.reserve((size_t)3 * nchains));
-  SACB_CUDA(e->h_flags.reserve((size_t)2 * nchains));
-  SACB_CUDA(cudaMemcpyAsync(e->h_sums.p, e->d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, e->stream));
-  SACB_CUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, sizeof(int) * 2 * nchains, cudaMemcpyDeviceToHost, e->stream));
-  SACB_CUDA(cudaStreamSynchronize(e->stream));
-  { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->last_ms[0] += ms; cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->last_ms[1] += ms; }
-  for (int c = 0; c < nchains; c++)
-    if (e->h_flags.p[c]) { set_error("final pass: predictor state became non-finite"); return SAC_E_UNSUPPORTED; }
-  // ---- serialise (WriteEncoded / WriteBlockHeader / EncodeProfile, libsac.cpp:507-578) ----
-  std::vector<uint8_t> payload;
-  for (int f = 0; f < nframes; f++) {
-    push32(out, (uint32_t)fw[f].n);
-    for (int i = 0; i < kProfileSize; i++) { uint32_t ix; std::memcpy(&ix, &fw[f].profile[i], 4); push32(out, ix); }
-    for (int ch = 0; ch < nch; ch++) {
-      int c = -1;
-      for (int q = 0; q < nchains; q++) if (cj[q] == f && cc[q] == ch) c = q;
-      const long long nb = e->h_sums.p[2 * nchains + c];
-      const int maxbpn = e->h_flags.p[nchains + c];
-      payload.resize((size_t)nb);
-      SACB_CUDA(cudaMemcpy(payload.data(), e->d_bytes.p + boff[c], (size_t)nb, cudaMemcpyDeviceToHost));
-      push32(out, (uint32_t)nb); push32(out, (uint32_t)fw[f].mean[ch]); push32(out, (uint32_t)fw[f].mm[2 * ch]); push32(out, (uint32_t)fw[f].mm[2 * ch + 1]);
-      push16(out, (uint16_t)(maxbpn & 0xff));
-      out.insert(out.end(), payload.begin(), payload.end());
-    }
-  }
+  // ---- whatever final passes are still outstanding, then collect and serialise in frame order ----
+  for (int f = 0; f < nframes; f++)
+    if (!fin[f].launched) { int rc = launch_final(f); if (rc) return rc; }
+  for (int f = 0; f < nframes; f++) { int rc = collect_final(f); if (rc) return rc; }
   return SAC_OK;
 }
 

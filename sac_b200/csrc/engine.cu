@@ -115,7 +115,23 @@ int fill_chain(ChainDesc &d, const HostParam &hp, int nch, int cc, int k, const 
 }
 
 // ---- Engine ----------------------------------------------------------------------------------------------------------
-int Engine::init(int dev)
+Engine *Engine::helper(int i)
+{
+  while ((int)helpers.size() <= i) {
+    Engine *h = new Engine();
+    if (h->init(device, this) != SAC_OK) { delete h; return nullptr; }
+    helpers.push_back(h);
+  }
+  return helpers[i];
+}
+long long Engine::total_launches() const
+{
+  long long t = launches;
+  for (const Engine *h : helpers) t += h->launches;
+  return t;
+}
+
+int Engine::init(int dev, const Engine *parent)
 {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
@@ -125,22 +141,36 @@ int Engine::init(int dev)
   if (dev < 0 || dev >= cnt) { set_error("device index out of range"); return SAC_E_ARG; }
   device = dev;
   SACB_CUDA(cudaSetDevice(dev));
-  SACB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (parent) {
+    int lo = 0, hi = 0;
+    SACB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SACB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi));
+    is_helper = true;
+  } else {
+    SACB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  }
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
+  if (parent) {
+    enc_smem_bytes = parent->enc_smem_bytes; ols_smem_bytes = parent->ols_smem_bytes; ols_smem_cap_bytes = parent->ols_smem_cap_bytes; smem_bytes = parent->smem_bytes;
+    bt = parent->bt;                                                 // shared device tables (owned by the parent)
+    return SAC_OK;
+  }
   SACB_CUDA(bt.init(stream));
   return SAC_OK;
 }
 void Engine::destroy()
 {
   cudaSetDevice(device);
+  for (Engine *h : helpers) { h->destroy(); delete h; }
+  helpers.clear();
   if (stream) cudaStreamSynchronize(stream);
   d_descs.release(); h_descs.release(); d_scratch.release(); d_scratch_ols.release(); d_plpc.release(); d_resid.release(); d_sums.release(); d_flags.release();
   h_sums.release(); h_flags.release(); d_bpjobs.release(); h_bpjobs.release(); d_csig0.release(); d_hist.release();
   d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release();
-  bt.destroy();
+  if (!is_helper) bt.destroy();
   for (auto &e : ev) if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr;
@@ -179,6 +209,18 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   for (size_t ji = 0; ji < jobs.size(); ji++)
     for (int cc = 0; cc < jobs[ji].win->nch; cc++, c++) ooff[c + 1] = ooff[c] + ((predictor_ols_scratch_doubles(ols_order(hps[ji], cc)) + 1) & ~1LL);
   SACB_CUDA(d_scratch_ols.reserve((size_t)ooff[nchains]));
+  // OLS kernel shared memory for this launch: work matrix always (fast LDL path), covariance too while both stay
+  // within the cap that still leaves two CTAs per SM
+  size_t need_w = 0, need_both = 0;
+  for (size_t ji = 0; ji < jobs.size(); ji++)
+    for (int cc = 0; cc < jobs[ji].win->nch; cc++) {
+      const size_t n = (size_t)ols_order(hps[ji], cc), ld = (n + 1) | 1, mat = (n + 1) * ld * 8;
+      need_w = std::max(need_w, mat); need_both = std::max(need_both, 2 * mat);
+    }
+  const size_t ols_head = predictor_ols_shared_bytes();
+  const size_t ols_cap = (size_t)ols_smem_cap_bytes;
+  int ols_smem = (int)std::max<size_t>(std::min(ols_head + need_both, ols_cap), std::min<size_t>(ols_head + need_w, 200 * 1024));
+  ols_smem = std::max(ols_smem, ols_smem_bytes);
   SACB_CUDA(d_plpc.reserve(stride * nchains));
   c = 0;
   for (size_t ji = 0; ji < jobs.size(); ji++) {
@@ -197,7 +239,7 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   }
   SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, ols_smem_bytes, stream));
+  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, ols_smem, stream));
   SACB_CUDA(cudaEventRecord(ev[1], stream));
   launches += 2; last_launches[0] += 2;                             // ols_kernel + cascade_kernel
   return SAC_OK;
@@ -308,7 +350,7 @@ void sac_engine_destroy(sac_engine *h)
   e->destroy();
   delete e;
 }
-long long sac_engine_launches(const sac_engine *h) { return reinterpret_cast<const Engine *>(h)->launches; }
+long long sac_engine_launches(const sac_engine *h) { return reinterpret_cast<const Engine *>(h)->total_launches(); }
 void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_launches)
 {
   const Engine *e = reinterpret_cast<const Engine *>(h);

@@ -71,7 +71,8 @@ struct Engine {           // sac_engine
   BitplaneTables bt;
   int smem_bytes = 72 * 1024;        // decode-direction kernel (predictor.cu)
   int enc_smem_bytes = 100 * 1024;   // cascade kernel (predictor_enc.cu): 2 CTAs per SM
-  int ols_smem_bytes = 36 * 1024;    // OLS kernel: 6 CTAs per SM; matrices up to n = 32 stay in shared memory
+  int ols_smem_bytes = 28 * 1024;    // OLS kernel, minimum request (both matrices up to n = 32)
+  int ols_smem_cap_bytes = 100 * 1024; // OLS kernel: above this the covariance goes to HBM scratch, the work matrix stays
   long long launches = 0;
   double last_ms[3] = {0, 0, 0};
   long long last_launches[3] = {0, 0, 0};
@@ -95,7 +96,14 @@ struct Engine {           // sac_engine
   DevBuf<uint8_t> d_bytes;        // payload / msb scratch
   PinBuf<int32_t> h_stage;        // pinned staging for sample uploads
 
-  int init(int dev);
+  // helper engines: own stream (high priority) and pools on the same device, used for the final pass of a frame
+  // while the main stream already searches the next frame; they share this engine's model tables
+  std::vector<Engine *> helpers;
+  bool is_helper = false;
+  Engine *helper(int i);
+  long long total_launches() const;
+
+  int init(int dev, const Engine *parent = nullptr);
   void destroy();
   // residuals of every chain of `jobs` into d_resid (layout: chain c at c*stride); returns 0
   int run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride);
@@ -110,6 +118,7 @@ cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_byt
 cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream);
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols);
 long long predictor_ols_scratch_doubles(int n_ols);
+size_t predictor_ols_shared_bytes();
 size_t predictor_enc_shared_bytes();
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream);

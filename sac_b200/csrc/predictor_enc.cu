@@ -98,6 +98,14 @@ __device__ __forceinline__ double dot5(const double (&x)[kMixN], const double *y
   return 0.0 + init;
 }
 
+#ifdef SACB_PROFILE_CASC
+#define CP(i) do { const long long c__ = clock64(); cp[i] += c__ - clast; clast = c__; } while (0)
+#define CP_DECL long long cp[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long clast = clock64()
+#else
+#define CP(i) do { } while (0)
+#define CP_DECL do { } while (0)
+#endif
+
 struct EncShared {
   // taps <-> S
   double part[kTapWarps][8];          // [warp][stage] dot, [warp][4+stage] power sum
@@ -233,12 +241,15 @@ __device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int 
   tap_load(r2, S.fpw[2], S.fmu[2], N2, tl);
   tap_load(r3, S.fpw[3], S.fmu[3], N3, tl);
   int p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+  CP_DECL;
   for (int t = 0; t < n; t++) {
+    CP(7);
     double acc[8];
     tap_dot(r0, h0, ow0, opw0, N0, p0, tl, acc[0], acc[4]);
     tap_dot(r1, h1, ow1, opw1, N1, p1, tl, acc[1], acc[5]);
     tap_dot(r2, h2, ow2, opw2, N2, p2, tl, acc[2], acc[6]);
     tap_dot(r3, h3, ow3, opw3, N3, p3, tl, acc[3], acc[7]);
+    CP(0);
 #pragma unroll
     for (int q = 0; q < 8; q++) acc[q] = butterfly(acc[q]);
     if (lane == 0) {
@@ -247,7 +258,9 @@ __device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int 
     }
     __threadfence_block();
     bar_arrive(kBarB1, 160);
+    CP(1);
     bar_sync(kBarB2, 160);
+    CP(2);
     const double g0 = ldd_vol(&S.wgrad[0]), g1 = ldd_vol(&S.wgrad[1]), g2 = ldd_vol(&S.wgrad[2]), g3 = ldd_vol(&S.wgrad[3]);
     tap_update(r0, h0, ow0, omu0, N0, p0, tl, g0);
     tap_update(r1, h1, ow1, omu1, N1, p1, tl, g1);
@@ -257,7 +270,12 @@ __device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int 
     p1 = p1 == 0 ? N1 : p1 - 1;
     p2 = p2 == 0 ? N2 : p2 - 1;
     p3 = p3 == 0 ? N3 : p3 - 1;
+    CP(3);
   }
+#ifdef SACB_PROFILE_CASC
+  if (tid == 0 && blockIdx.x < 2)
+    printf("chain %d taps: clk/sample dot %.0f reduce+arrive %.0f wait_S %.0f update %.0f\n", blockIdx.x, (double)cp[0] / n, (double)cp[1] / n, (double)cp[2] / n, (double)cp[3] / n);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -273,6 +291,7 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
   int pos = 0;
   bool bad = false;
   const double *plpc = d.plpc;
+  CP_DECL;
   int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
   int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
   double lcur = lane < n ? __ldg(plpc + lane) : 0.0;
@@ -293,8 +312,11 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
       wi[i] = dmax(0.0 + ((0.0 + v0[i] * sw0) + v1[i] * sw1), 0.0);
     }
     const double target = val - p_lpc;
+    CP(0);
     if (t) bar_sync(kBarB4, 64);                             // p_rls for this sample
+    CP(1);
     bar_sync(kBarB1, 160);                                   // tap partial sums
+    CP(2);
     if (lane < 8) {
       const double v = (ldd_vol(&S.part[0][lane]) + ldd_vol(&S.part[1][lane])) + (ldd_vol(&S.part[2][lane]) + ldd_vol(&S.part[3][lane]));
       if (lane < 4) S.p[lane] = v; else S.spow[lane - 4] = v;
@@ -333,6 +355,7 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
     __threadfence_block();
     bar_arrive(kBarB2, 160);
     bar_arrive(kBarB3, 64);
+    CP(3);
     // ---- hand px to the bias warp ----
     if (t >= kQ) spin_until_gt(&S.q2_con, t - kQ);
     if (lane == 0) { S.q2[t & (kQ - 1)] = px; __threadfence_block(); st_vol(&S.q2_pub, t + 1); }
@@ -361,7 +384,12 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
       if (lane == 0) { S.rsum[0] = r0; S.rsum[1] = r1; S.sw[0] = w0 * inv_total; S.sw[1] = w1 * inv_total; }
       __syncwarp();
     }
+    CP(4);
   }
+#ifdef SACB_PROFILE_CASC
+  if (lane == 0 && blockIdx.x < 2)
+    printf("chain %d S: clk/sample pre %.0f wait_R %.0f wait_taps %.0f crit %.0f post(mix update) %.0f\n", blockIdx.x, (double)cp[0] / n, (double)cp[1] / n, (double)cp[2] / n, (double)cp[3] / n, (double)cp[4] / n);
+#endif
   if (lane == 0 && d.flags) *d.flags = bad ? 1 : 0;
 }
 
@@ -657,38 +685,41 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
             if (dn < 1e-12) ok_next = false;
             inv_next = 1.0 / dn;
           }
+          // trailing update: per lane a 4 x 4 register tile per 32 x 64 block (8 x 16 lane grid)
           for (int rb = 0; rb < m; rb += 32) {
-            for (int cb = 0; cb <= rb && cb < m - 1; cb += 32) {
+            for (int cb = 0; cb < m - 1 && cb <= rb + 31; cb += 64) {
               const uint32_t rbase = pjj + (uint32_t)rb * ldb + r0;
               const uint32_t cbase = (uint32_t)cb * 8u + q0;
-              bool rv[4], cv[2];
-              double al[4], cj[2], e[4][2];
+              // validity: row rel <= m, column rel <= m-1, column <= row, and not the next pivot (1,1)
+              const int rr0 = rb + 1 + ra, qq0 = cb + 1 + ca;
+              const int delta = qq0 - rr0;                         // element (a,b) is on/below the diagonal iff 8a - 16b >= delta
+              bool rv[4], cv[4];
+              double al[4], cj[4], e[4][4];
 #pragma unroll
-              for (int a = 0; a < 4; a++) { rv[a] = rb + 1 + ra + 8 * a <= m; al[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep) : 0.0; }
+              for (int a = 0; a < 4; a++) { rv[a] = rr0 + 8 * a <= m; al[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep) : 0.0; }
 #pragma unroll
-              for (int b = 0; b < 2; b++) {
-                cv[b] = cb + 1 + ca + 16 * b <= m - 1;
-                cj[b] = cv[b] ? lds_f64(pjj + (uint32_t)(cb + 1 + ca + 16 * b) * ldb) : 0.0;
+              for (int b = 0; b < 4; b++) {
+                cv[b] = qq0 + 16 * b <= m - 1;
+                cj[b] = cv[b] ? lds_f64(pjj + (uint32_t)(qq0 + 16 * b) * ldb) : 0.0;
               }
-              bool on[4][2];
+              bool on[4][4];
 #pragma unroll
               for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int b = 0; b < 2; b++) {
-                  const int rr = rb + 1 + ra + 8 * a, qq = cb + 1 + ca + 16 * b;
-                  on[a][b] = rv[a] && cv[b] && qq <= rr && !(rr == 1 && qq == 1);
+                for (int b = 0; b < 4; b++) {
+                  on[a][b] = rv[a] && cv[b] && (8 * a - 16 * b >= delta) && !(a == 0 && b == 0 && rr0 == 1 && qq0 == 1);
                   e[a][b] = on[a][b] ? lds_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u) : 0.0;
                 }
 #pragma unroll
               for (int a = 0; a < 4; a++) {
                 const double la = al[a] * inv;
 #pragma unroll
-                for (int b = 0; b < 2; b++) e[a][b] = __fma_rn(-la, cj[b], e[a][b]);
+                for (int b = 0; b < 4; b++) e[a][b] = __fma_rn(-la, cj[b], e[a][b]);
               }
 #pragma unroll
               for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int b = 0; b < 2; b++)
+                for (int b = 0; b < 4; b++)
                   if (on[a][b]) sts_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u, e[a][b]);
             }
           }
@@ -773,7 +804,7 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTeam, 6) ols_kernel(const ChainDesc *__restrict__ descs)
+__global__ void __launch_bounds__(kTeam, 5) ols_kernel(const ChainDesc *__restrict__ descs)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ChainDesc &d = descs[blockIdx.x];
@@ -887,6 +918,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc
 } // namespace
 
 size_t predictor_enc_shared_bytes() { return (sizeof(EncShared) + 15) & ~size_t(15); }
+size_t predictor_ols_shared_bytes() { return (sizeof(OlsShared) + 15) & ~size_t(15); }
 
 // doubles of HBM scratch a chain may need when nothing but the fixed blocks fit shared memory
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols)
