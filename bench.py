@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--gen", type=int, default=int(os.environ.get("SAC_BENCH_GEN", "128")), help="DDS generation size (GPU batch per frame)")
     ap.add_argument("--nfunc", type=int, default=1000, help="DDS evaluations per frame (--best: 1000)")
     ap.add_argument("--seconds", type=int, default=60)
+    ap.add_argument("--inflight", type=int, default=3, help="frames encoded concurrently per GPU (one stream each); 1 = sequential with warm start")
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=3, help="steps of the end-to-end leg (host buffers)")
     return ap.parse_args()
 
 
@@ -201,7 +203,8 @@ def main():
     import oracle_lib as ol   # analyse() only (mean / min / max on the host, numpy)
     frames = stream_frames(args.seconds, 3 + rank)
     nfr = len(frames)
-    cfg = sb.make_cfg("best", num_threads=args.gen, maxnfunc=args.nfunc)
+    # frames of the stream are independent searches (--opt-reset semantics) and run concurrently, one stream each
+    cfg = sb.make_cfg("best", num_threads=args.gen, maxnfunc=args.nfunc, frame_parallel=2 if args.inflight > 1 else 0, reset=1)
     # device-resident copies for the `value` leg
     wins, means = [], []
     for fr in frames:
@@ -218,23 +221,26 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    kernel_ms = [0.0, 0.0, 0.0]; kernel_launches = [0, 0, 0]
     out_bytes = {}
-    prof = None
 
     def run_steps(count, resident, first):
-        nonlocal prof
-        for s in range(count):
-            f = (first + s) % nfr
-            if f == 0:
-                prof = None                      # a new stream starts from the base profile
+        """`count` steps = `count` consecutive frames of the stream (cyclic), `inflight` of them per call"""
+        s = 0
+        while s < count:
+            g = min(args.inflight, count - s)
+            fs = [(first + s + i) % nfr for i in range(g)]
             if resident:
-                rec, prof = eng.frames_encode_resident(cfg, [wins[f]], [means[f]], FRAME, prof)
+                rec, _ = eng.frames_encode_resident(cfg, [wins[f] for f in fs], [means[f] for f in fs], FRAME, None)
             else:
-                rec, prof = eng.frames_encode(cfg, [pinned_np[f]], FRAME, prof)
-            out_bytes[f] = rec.tobytes()
+                rec, _ = eng.frames_encode(cfg, [pinned_np[f] for f in fs], FRAME, None)
+            pos = 0
+            for f in fs:            # split the concatenated frame records (u32 numsamples, 58 f32, per channel 18 B header + payload)
+                p0 = pos; pos += 4 + 58 * 4
+                for ch in range(2):
+                    nb = int(np.frombuffer(rec[pos:pos + 4].tobytes(), "<u4")[0]); pos += 18 + nb
+                out_bytes[f] = rec[p0:pos].tobytes()
+            s += g
 
-    launches0 = eng.launches
     run_steps(args.warmup, True, 0)
     barrier()
     sampler.start()
@@ -244,14 +250,14 @@ def main():
     barrier()
     t_val = time.perf_counter() - t0
     l_timed = eng.launches - l_before
-    # e2e leg
+    # e2e leg: the same steps from pinned HOST planes through sac_frames_encode (H2D of the planes, D2H of the payload inside)
     barrier()
     t0 = time.perf_counter()
-    run_steps(args.steps, False, args.warmup)
+    run_steps(args.e2e_steps, False, args.warmup)
     barrier()
     t_e2e = time.perf_counter() - t0
     sampler.stop_flag = True
-    # kernel-class timing of one representative generation for the roofline (CUDA events inside the engine)
+    # kernel-class timing of one representative generation for the roofline (CUDA events on the engine's stream)
     _, _, vdef = sb.base_profile()
     x0 = np.tile(vdef[sb.SEARCH_DIMS].astype(np.float64), (args.gen, 1))
     eng.eval_population(wins[0], 220500, 441000, vdef, x0, sb.COST_BITPLANE, 4)
@@ -260,9 +266,8 @@ def main():
     ms, ln = eng.last_timing()
     fp64_peak = eng.fp64_peak_gflops()
     t_val = shard.max_over_ranks(t_val, dev); t_e2e = shard.max_over_ranks(t_e2e, dev)
-    total_samples = FRAME * args.steps * world
-    value = total_samples / t_val / 1e6
-    e2e = total_samples / t_e2e / 1e6
+    value = FRAME * args.steps * world / t_val / 1e6
+    e2e = FRAME * args.e2e_steps * world / t_e2e / 1e6
     # bitstream gather (outside the timed region): the only collective of the path. Unit f*world+rank = frame f of rank's stream
     gathered = None
     if world > 1:
@@ -271,16 +276,21 @@ def main():
         gathered = shard.gather_bitstreams(local_units, n_units, rank, world, dev)
     if rank == 0:
         chains = 2 * args.gen
+        W = 441000
         f0, f1 = algorithmic_flops_per_sample(vdef, 4)
-        flops = (f0 + f1) * 441000 * args.gen
-        pred_s, bp_s = ms[0] * 1e-3, ms[1] * 1e-3
-        dominant = "predictor_kernel" if pred_s >= bp_s else "bitplane_encode_kernel"
-        if pred_s >= bp_s:
-            alg_bytes = chains * 441000 * (4 + 4)            # window read (int32) + residual write per chain-sample
-            dur = pred_s
-        else:
-            alg_bytes = chains * 441000 * 4 * 2 + chains * 8  # residual read + in-place S2U write, cost out
-            dur = bp_s
+        flops = (f0 + f1) * W * args.gen
+        ols_s, casc_s, bp_s = ms[3] * 1e-3, (ms[0] - ms[3]) * 1e-3, ms[1] * 1e-3
+        planes_coded = 15                                         # maxbpn + 1 of the synthetic streams' residuals
+        kern = {
+            # algorithmic HBM bytes per chain-sample: own + other plane in (2 x 4 B), p_lpc out (8 B)
+            "ols_kernel": (ols_s, chains * W * 16),
+            # sample in (4 B), p_lpc in (8 B), residual out (4 B)
+            "cascade_kernel": (casc_s, chains * W * 16),
+            # residual in + S2U-mapped back in place (8 B), then one 4-B read per coded plane, cost out
+            "bitplane_pipe_kernel": (bp_s, chains * W * (8 + 4 * planes_coded) + chains * 8),
+        }
+        dominant = max(kern, key=lambda k: kern[k][0])
+        dur, alg_bytes = kern[dominant]
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -296,27 +306,31 @@ def main():
             cbo = {"value": None, "unit": "MSamples/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
         h2d = FRAME * 2 * 4
         d2h = int(np.mean([len(b) for b in out_bytes.values()]))
+        pred_s = ols_s + casc_s
         line = {
             "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_val / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3+rank), --best; step = one 20-s frame "
-                                   "(882000 sample-frames): DDS %d evaluations in generations of %d (run_mt/SSC1), window 441000, "
-                                   "CostBitplane, k=4; final pass k=1 + bitplane payload" % (args.nfunc, args.gen),
-                       "generation": args.gen, "nfunc": args.nfunc, "frames": nfr,
-                       "l2": "inputs per step (7 MB planes + per-chain state >> 126 MB L2 across a generation) exceed L2; no flush"},
+            "config": {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3+rank), --best --opt-reset; step = one 20-s frame "
+                                   "(882000 sample-frames): DDS %d evaluations in generations of %d (--opt-cfg=dds,%d: run_mt/SSC1), window 441000, "
+                                   "CostBitplane, k=4; final pass k=1 + bitplane payload; %d frames in flight per GPU (one stream each)"
+                                   % (args.nfunc, args.gen, args.gen, args.inflight),
+                       "generation": args.gen, "nfunc": args.nfunc, "frames": nfr, "frames_in_flight": args.inflight, "e2e_steps": args.e2e_steps,
+                       "l2": "inputs per step (7 MB planes + 3.5 MB of p_lpc and 1.7 MB of residuals per chain, 256 chains per generation) "
+                             "exceed the 126 MB L2; no flush"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(l_timed),
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
-                         "note": "this path is a serial fp64/integer recurrence, not HBM-bound: see fp64 and DESIGN.md section 5; "
-                                 "peak = MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
-            "fp64": {"kernel": "predictor_kernel", "achieved_gflops": flops / pred_s / 1e9 if pred_s > 0 else None,
+                         "note": "the path is a set of serial fp64/integer recurrences bound by instruction latency, not by HBM: "
+                                 "see `fp64` and DESIGN.md section 5; peak = MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
+            "fp64": {"kernel": "ols_kernel + cascade_kernel", "achieved_gflops": flops / pred_s / 1e9 if pred_s > 0 else None,
                      "peak_gflops": fp64_peak, "frac": (flops / pred_s / 1e9) / fp64_peak if pred_s > 0 and fp64_peak > 0 else None,
                      "peak_how": "measured in this run: 8 independent DFMA chains/thread, 1184x256 threads, CUDA events",
                      "flops_per_stereo_sample": f0 + f1},
-            "kernel_ms_per_generation": {"predictor": ms[0], "bitplane": ms[1], "chains": chains, "window": 441000},
+            "kernel_ms_per_generation": {"ols": ms[3], "cascade": ms[0] - ms[3], "bitplane": ms[1], "chains": chains, "window": W,
+                                         "profile": "default (one generation of identical default-profile candidates, device alone)"},
             "cpu_baseline": cbo,
             "gathered_bytes": (sum(len(b) for b in gathered) if gathered is not None else None),
             "bytes_per_frame": d2h, "bps": 8.0 * sum(len(b) for b in out_bytes.values()) / (len(out_bytes) * FRAME * 2),

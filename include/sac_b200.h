@@ -46,7 +46,7 @@ void sac_engine_destroy(sac_engine *);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 long long sac_engine_launches(const sac_engine *);
 /* device time (ms, CUDA events on the engine's stream) and launches of the last call, by kernel class:
- * [0] predictor [1] bitplane [2] entropy/other; out_ms[3], out_launches[3] */
+ * [0] predictor (ols_kernel + cascade_kernel) [1] bitplane [2] entropy/other [3] ols_kernel alone; out_ms[4], out_launches[4] */
 void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_launches);
 
 /* measured DFMA throughput of the device (GFLOP/s, 2 flop per fma; CUDA events): the fp64 roofline denominator */
@@ -109,7 +109,8 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
   int sparse_pcm;               /* accepted for CLI compatibility; sparse mapping is not implemented (never smaller below ratio 1.05) */
   int max_framelen;             /* seconds (20) */
   int adapt_block;              /* accepted; adaptive splitting is not implemented (one sub-frame per read) */
-  int frame_parallel;           /* B200 extension: search all frames of a call concurrently (implies reset semantics) */
+  int frame_parallel;           /* B200 extension (implies --opt-reset semantics): 1 = all frames of a call share each generation's launches,
+                                   2 = every frame runs on its own stream / host thread, all concurrently on the GPU */
   int verbose;
 } sac_cfg;
 void sac_cfg_default(sac_cfg *);

@@ -193,7 +193,7 @@ class Engine:
         return int(lib().sac_engine_launches(self.h))
 
     def last_timing(self):
-        ms = (C.c_double * 3)(); ln = (C.c_longlong * 3)()
+        ms = (C.c_double * 4)(); ln = (C.c_longlong * 4)()
         lib().sac_engine_last_timing(self.h, ms, ln)
         return list(ms), list(ln)
 

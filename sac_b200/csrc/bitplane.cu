@@ -956,29 +956,26 @@ void BitplaneTables::destroy()
   d_stretch = nullptr; d_squash = nullptr; d_laplace = nullptr;
 }
 
+cudaError_t bitplane_init_attributes()
+{
+  const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
+  const int psmem = (int)sizeof(PipeShared) + kStretchBytes + kSquashBytes;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bitplane_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(bitplane_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+}
+
 cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int njobs, int mode, cudaStream_t stream)
 {
   Tables T{bt.d_stretch, bt.d_squash, bt.d_laplace, bt.lap_bits};
   const int grid = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
   const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(bitplane_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    attr = true;
-  }
   static const bool use_pipe = !(getenv("SAC_B200_BP_PIPE") && atoi(getenv("SAC_B200_BP_PIPE")) == 0);
   if (mode != 2 && use_pipe) {
     const int psmem = (int)sizeof(PipeShared) + kStretchBytes + kSquashBytes;
-    static bool pattr = false;
-    if (!pattr) {
-      cudaError_t e;
-      if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
-      if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
-      pattr = true;
-    }
     if (mode == 0) bitplane_pipe_kernel<0><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
     else bitplane_pipe_kernel<1><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
     return cudaGetLastError();

@@ -33,6 +33,7 @@ struct BitplaneTables {
 // mode 0: byte count only (CostBitplane), 1: emit payload, 2: decode
 cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int njobs, int mode, cudaStream_t stream);
 size_t bitplane_state_bytes();
+cudaError_t bitplane_init_attributes();
 void compute_logdomain_tables(int16_t *stretch /*[32768]*/, int16_t *squash /*[4095]*/);
 
 } // namespace sacb

@@ -15,7 +15,10 @@
 #include <cstring>
 #include <fstream>
 #include <limits>
+#include <array>
 #include <memory>
+#include <string>
+#include <thread>
 
 namespace sacb {
 
@@ -286,9 +289,62 @@ void analyse_channel(std::vector<int32_t> &s, int zero_mean, int32_t &mean, int3
 
 } // namespace
 
+static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
+                             const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
+                             const sac_window *const *resident = nullptr, const int32_t *resident_means = nullptr);
+
+// frame_parallel == 2: every frame of the call is encoded by its own host thread on its own helper engine (own
+// stream and pools), all concurrently on this GPU. A single frame's kernels are bound by their slowest chain and
+// leave most of the machine idle; several frames in flight fill it. Frames start from the base profile (the
+// reference's --opt-reset semantics, cmdline.cpp:193).
+static int frames_encode_streams(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
+                                 const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
+                                 const sac_window *const *resident, const int32_t *resident_means)
+{
+  const int kMaxPar = 4;
+  const int kBase = 8;                                               // helper slots 0..3 serve final passes of the main engine
+  std::vector<std::vector<uint8_t>> outs(nframes);
+  std::vector<int> rcs(nframes, SAC_OK);
+  std::vector<std::string> errs(nframes);
+  std::vector<std::array<float, kProfileSize>> profs(nframes);
+  sac_cfg one = cfg;
+  one.frame_parallel = 0; one.reset = 1;
+  for (int i = 0; i < std::min(kMaxPar, nframes); i++) if (!e->helper(kBase + i)) return SAC_E_CUDA;
+  for (int f0 = 0; f0 < nframes; f0 += kMaxPar) {
+    const int f1 = std::min(nframes, f0 + kMaxPar);
+    std::vector<std::thread> th;
+    for (int f = f0; f < f1; f++) {
+      th.emplace_back([&, f]() {
+        Engine *h = e->helpers[kBase + (f - f0)];
+        cudaSetDevice(h->device);
+        for (int i = 0; i < kProfileSize; i++) profs[f][i] = kBaseProfile[i][2];
+        rcs[f] = frames_encode_seq(h, one, nch, max_framesize, 1, planes ? planes + (size_t)f * nch : nullptr, numsamples ? numsamples + f : nullptr,
+                                   profs[f].data(), outs[f], resident ? resident + f : nullptr, resident_means ? resident_means + (size_t)f * nch : nullptr);
+        if (rcs[f]) errs[f] = sac_last_error();
+      });
+    }
+    for (auto &t : th) t.join();
+  }
+  for (int f = 0; f < nframes; f++) {
+    if (rcs[f]) { set_error(errs[f]); return rcs[f]; }
+    out.insert(out.end(), outs[f].begin(), outs[f].end());
+  }
+  std::memcpy(profile_io, profs[nframes - 1].data(), sizeof(float) * kProfileSize);
+  return SAC_OK;
+}
+
 static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
                          const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                          const sac_window *const *resident = nullptr, const int32_t *resident_means = nullptr)
+{
+  if (cfg.frame_parallel == 2 && nframes > 1)
+    return frames_encode_streams(e, cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, out, resident, resident_means);
+  return frames_encode_seq(e, cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, out, resident, resident_means);
+}
+
+static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_framesize, int nframes, const int32_t *const *planes,
+                             const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
+                             const sac_window *const *resident, const int32_t *resident_means)
 {
   std::vector<FrameWork> fw(nframes);
   struct Cleanup { std::vector<FrameWork> &f; bool own; ~Cleanup() { if (own) for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw, resident == nullptr};
@@ -397,9 +453,9 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
   auto base_reset = [&](float *p) { for (int i = 0; i < kProfileSize; i++) p[i] = kBaseProfile[i][2]; };
 
   if (cfg.optimize && cfg.maxnfunc > 0 && cfg.fraction > 0.0) {
-    const int groups = cfg.frame_parallel ? 1 : nframes;          // frames searched together per group
+    const int groups = cfg.frame_parallel == 1 ? 1 : nframes;     // frames searched together per group
     for (int g = 0; g < groups; g++) {
-      const int f0 = cfg.frame_parallel ? 0 : g, f1 = cfg.frame_parallel ? nframes : g + 1;
+      const int f0 = cfg.frame_parallel == 1 ? 0 : g, f1 = cfg.frame_parallel == 1 ? nframes : g + 1;
       std::vector<std::unique_ptr<DdsSearch>> ss;
       std::vector<int> wfrom, wn;
       for (int f = f0; f < f1; f++) {

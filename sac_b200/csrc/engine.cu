@@ -141,6 +141,17 @@ int Engine::init(int dev, const Engine *parent)
   if (dev < 0 || dev >= cnt) { set_error("device index out of range"); return SAC_E_ARG; }
   device = dev;
   SACB_CUDA(cudaSetDevice(dev));
+  {
+    // dynamic shared-memory limits of every kernel, once per process (launches come from several host threads)
+    static std::once_flag once_dev[64];
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once_dev[dev & 63], [] {
+      attr_err = predictor_enc_init_attributes();
+      if (attr_err == cudaSuccess) attr_err = predictor_init_attributes();
+      if (attr_err == cudaSuccess) attr_err = bitplane_init_attributes();
+    });
+    SACB_CUDA(attr_err);
+  }
   if (parent) {
     int lo = 0, hi = 0;
     SACB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -177,7 +188,7 @@ void Engine::destroy()
 }
 void Engine::begin_call()
 {
-  for (int i = 0; i < 3; i++) { last_ms[i] = 0; last_launches[i] = 0; }
+  for (int i = 0; i < 4; i++) { last_ms[i] = 0; last_launches[i] = 0; }
 }
 
 int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride)
@@ -217,6 +228,11 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
       const size_t n = (size_t)ols_order(hps[ji], cc), ld = (n + 1) | 1, mat = (n + 1) * ld * 8;
       need_w = std::max(need_w, mat); need_both = std::max(need_both, 2 * mat);
     }
+  // cascade kernel: histories and overflow taps of the largest chain, capped so that two CTAs still fit an SM
+  size_t casc_need = 0;
+  for (size_t ji = 0; ji < jobs.size(); ji++)
+    for (int cc = 0; cc < jobs[ji].win->nch; cc++) casc_need = std::max(casc_need, (size_t)predictor_enc_smem_doubles(hps[ji].vn[cc]) * 8);
+  const int casc_smem = (int)std::min<size_t>(predictor_enc_shared_bytes() + casc_need + 64, (size_t)enc_smem_bytes);
   const size_t ols_head = predictor_ols_shared_bytes();
   const size_t ols_cap = (size_t)ols_smem_cap_bytes;
   int ols_smem = (int)std::max<size_t>(std::min(ols_head + need_both, ols_cap), std::min<size_t>(ols_head + need_w, 200 * 1024));
@@ -239,7 +255,7 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   }
   SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, enc_smem_bytes, ols_smem, stream));
+  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, casc_smem, ols_smem, stream, ev[4]));
   SACB_CUDA(cudaEventRecord(ev[1], stream));
   launches += 2; last_launches[0] += 2;                             // ols_kernel + cascade_kernel
   return SAC_OK;
@@ -314,7 +330,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
       ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : v;
     }
   } else { set_error("unknown cost kind"); return SAC_E_ARG; }
-  { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms; }
+  { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms; cudaEventElapsedTime(&ms, ev[0], ev[4]); last_ms[3] += ms; last_launches[3]++; }
   for (size_t j = 0; j < jobs.size(); j++) cost[j] = 0.0;
   // sum over channels (FrameCoder::GetCost, libsac.cpp:358-361; a two-term sum is order-independent)
   for (int c = 0; c < nchains; c++) cost[chain_job[c]] += ccost[c];
@@ -354,7 +370,7 @@ long long sac_engine_launches(const sac_engine *h) { return reinterpret_cast<con
 void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_launches)
 {
   const Engine *e = reinterpret_cast<const Engine *>(h);
-  for (int i = 0; i < 3; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
+  for (int i = 0; i < 4; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
 }
 
 double sac_fp64_peak_gflops(sac_engine *h)

@@ -67,15 +67,15 @@ struct Job {
 struct Engine {           // sac_engine
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // ev[4]: between ols_kernel and cascade_kernel
   BitplaneTables bt;
   int smem_bytes = 72 * 1024;        // decode-direction kernel (predictor.cu)
-  int enc_smem_bytes = 100 * 1024;   // cascade kernel (predictor_enc.cu): 2 CTAs per SM
+  int enc_smem_bytes = 100 * 1024;   // cascade kernel (predictor_enc.cu): cap of the per-launch request, 2 CTAs per SM
   int ols_smem_bytes = 28 * 1024;    // OLS kernel, minimum request (both matrices up to n = 32)
   int ols_smem_cap_bytes = 100 * 1024; // OLS kernel: above this the covariance goes to HBM scratch, the work matrix stays
   long long launches = 0;
-  double last_ms[3] = {0, 0, 0};
-  long long last_launches[3] = {0, 0, 0};
+  double last_ms[4] = {0, 0, 0, 0};          // predictor (ols + cascade), bitplane, other cost kernels, ols alone
+  long long last_launches[4] = {0, 0, 0, 0};
 
   DevBuf<ChainDesc> d_descs;
   PinBuf<ChainDesc> h_descs;
@@ -115,10 +115,14 @@ struct Engine {           // sac_engine
 
 // kernels (predictor.cu, cost.cu)
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream);
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream,
+                                 cudaEvent_t between = nullptr);
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols);
 long long predictor_ols_scratch_doubles(int n_ols);
 size_t predictor_ols_shared_bytes();
+long long predictor_enc_smem_doubles(const int *vn);
+cudaError_t predictor_enc_init_attributes();
+cudaError_t predictor_init_attributes();
 size_t predictor_enc_shared_bytes();
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,
                            size_t hist_stride, double *out, cudaStream_t stream);

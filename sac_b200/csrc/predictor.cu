@@ -555,15 +555,15 @@ __global__ void __launch_bounds__(kBlockThreads, 3) predictor_kernel(const Chain
 
 size_t predictor_scalar_bytes() { return (sizeof(Scalar) + 15) & ~size_t(15); }
 
+cudaError_t predictor_init_attributes()
+{
+  cudaError_t e = cudaFuncSetAttribute(predictor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(predictor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+}
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream)
 {
-  static bool attr_set[2] = {false, false};
   auto kern = decode ? predictor_kernel<true> : predictor_kernel<false>;
-  if (!attr_set[decode]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    if (e != cudaSuccess) return e;
-    attr_set[decode] = true;
-  }
   kern<<<nchains, kBlockThreads, smem_bytes, stream>>>(d_descs);
   return cudaGetLastError();
 }

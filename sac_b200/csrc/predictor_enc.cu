@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <cstddef>
+#include <cstdio>
 
 namespace sacb {
 
@@ -41,7 +42,8 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kEncThreads = 256;                        // cascade kernel: 2 warpgroups: taps | S, B, R
-constexpr int kTeam = 128;                              // OLS kernel: one team of 4 warps
+constexpr int kTeam = 128;
+constexpr int kMaxDynSmem = 227 * 1024;                              // OLS kernel: one team of 4 warps
 constexpr int kR0 = 12, kR1 = 4, kR2 = 2, kR3 = 1;   // register-resident tap slots per thread and stage
 constexpr int kQ = 32;                                // ring depth (samples)
 constexpr int kXW = 256;                              // input window (samples, power of two)
@@ -927,6 +929,14 @@ long long predictor_enc_scratch_doubles(const int *vn, int n_ols)
   for (int s = 0; s < kStages; s++) t += 6LL * vn[s] + 1;
   return t + 16;
 }
+// doubles of shared memory that keep every array of a chain on chip (histories + taps beyond the register slots)
+long long predictor_enc_smem_doubles(const int *vn)
+{
+  const int regs[kStages] = {kR0, kR1, kR2, kR3};
+  long long t = 0;
+  for (int s = 0; s < kStages; s++) t += (vn[s] + 1) + 3LL * (vn[s] > kTapThreads * regs[s] ? vn[s] - kTapThreads * regs[s] : 0);
+  return t;
+}
 long long predictor_ols_scratch_doubles(int n_ols)
 {
   const long long ld = (n_ols + 1) | 1;
@@ -934,22 +944,19 @@ long long predictor_ols_scratch_doubles(int n_ols)
 }
 
 // residuals of every chain: OLS predictions first (ols_kernel -> ChainDesc::plpc), then the cascade
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream)
+cudaError_t predictor_enc_init_attributes()
 {
-  static int attr_smem = 0, attr_ols = 0;
-  if (attr_smem < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem_bytes;
-  }
-  if (attr_ols < ols_smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ols_smem_bytes);
-    if (e != cudaSuccess) return e;
-    attr_ols = ols_smem_bytes;
-  }
+  cudaError_t e = cudaFuncSetAttribute(cascade_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
+cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream,
+                                 cudaEvent_t between)
+{
   ols_kernel<<<nchains, kTeam, ols_smem_bytes, stream>>>(d_descs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess) return e;
   cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs);
   return cudaGetLastError();
 }

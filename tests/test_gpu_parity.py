@@ -211,15 +211,20 @@ def test_file_roundtrip_with_metadata(engine, nch, sampwidth, n, sr):
 
 
 def test_multi_frame_profile_chain_and_frame_parallel(engine):
-    """frames of one stream: sequential warm start (reference semantics) and the frame-parallel extension both decode"""
+    """frames of one stream: sequential warm start (reference semantics, final pass overlapped with the next search) and
+    the two frame-parallel extensions (1: shared launches, 2: one stream + host thread per frame) all decode; the
+    frame-parallel modes search every frame from the base profile, so they agree with each other byte for byte"""
     pcm = synth_pcm(1.5, 2, 77).astype(np.int32)
     frames = [[pcm[:22050, 0], pcm[:22050, 1]], [pcm[22050:44100, 0], pcm[22050:44100, 1]], [pcm[44100:, 0], pcm[44100:, 1]]]
-    for fp in (0, 1):
+    recs = {}
+    for fp in (0, 1, 2):
         cfg = sb.make_cfg(None, optimize=1, fraction=0.005, maxnfunc=6, num_threads=5, sigma=0.2, cost_kind=2, frame_parallel=fp, max_framelen=1)
         rec, prof = engine.frames_encode(cfg, frames, 44100)
+        recs[fp] = rec.tobytes()
         pos = 0
         for fr in frames:
             dec, used = engine.frame_decode(2, rec[pos:], 44100)
             assert all(np.array_equal(dec[ch], fr[ch]) for ch in range(2))
             pos += used
         assert pos == len(rec)
+    assert recs[1] == recs[2]
