@@ -474,17 +474,22 @@ __device__ __forceinline__ uint32_t counter_upd_s(const uint16_t *divtab, uint32
   return (uint32_t)p1 | ((uint32_t)cnt << 16);
 }
 
-constexpr int kPipeThreads = 128;
+constexpr int kPipeThreads = 128;                                  // threads per stream (4 pipeline warps)
+constexpr int kPipeStreams = 2;                                    // streams per CTA: they share the 72 KB of LogDomain tables
 
 template <int MODE>
-__global__ void __launch_bounds__(kPipeThreads) bitplane_pipe_kernel(const BpJob *__restrict__ jobs, Tables TG)
+__global__ void __launch_bounds__(kPipeThreads * kPipeStreams) bitplane_pipe_kernel(const BpJob *__restrict__ jobs, int njobs, Tables TG)
 {
   extern __shared__ __align__(16) unsigned char bp_smem[];
   const Tables T = stage_tables(TG, bp_smem);
-  PipeShared &P = *reinterpret_cast<PipeShared *>(bp_smem + kStretchBytes + kSquashBytes);
+  const int sidx = threadIdx.x / kPipeThreads;                     // stream of this CTA
+  const int job = blockIdx.x * kPipeStreams + sidx;
+  PipeShared &P = reinterpret_cast<PipeShared *>(bp_smem + kStretchBytes + kSquashBytes)[sidx];
   BpState &S = P.st;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const BpJob J = jobs[blockIdx.x];
+  const int tid = threadIdx.x - sidx * kPipeThreads, lane = tid & 31, warp = tid >> 5;
+  if (job >= njobs) return;
+  const BpJob J = jobs[job];
+  const int sbar = 1 + sidx;                                       // named barrier of this stream
   const int n = J.n;
   int32_t *u = J.buf;
 
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(kPipeThreads) bitplane_pipe_kernel(const BpJob
     const uint4 v4 = make_uint4(c0, c0, c0, c0);
     for (int i = tid; i < 65536 / 4; i += kPipeThreads) c4[i] = v4;
   }
-  __syncthreads();
+  asm volatile("bar.sync %0, %1;" ::"r"(sbar), "r"(kPipeThreads) : "memory");
   vmax = max(max(P.red[0], P.red[1]), max(P.red[2], P.red[3]));
   const int maxbpn = J.maxbpn >= 0 ? J.maxbpn : max(topbit(vmax), 0);
   const int nchunks = (n + 31) >> 5;
@@ -959,7 +964,7 @@ void BitplaneTables::destroy()
 cudaError_t bitplane_init_attributes()
 {
   const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
-  const int psmem = (int)sizeof(PipeShared) + kStretchBytes + kSquashBytes;
+  const int psmem = (int)sizeof(PipeShared) * kPipeStreams + kStretchBytes + kSquashBytes;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
@@ -975,9 +980,10 @@ cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int n
   const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
   static const bool use_pipe = !(getenv("SAC_B200_BP_PIPE") && atoi(getenv("SAC_B200_BP_PIPE")) == 0);
   if (mode != 2 && use_pipe) {
-    const int psmem = (int)sizeof(PipeShared) + kStretchBytes + kSquashBytes;
-    if (mode == 0) bitplane_pipe_kernel<0><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
-    else bitplane_pipe_kernel<1><<<njobs, kPipeThreads, psmem, stream>>>(d_jobs, T);
+    const int psmem = (int)sizeof(PipeShared) * kPipeStreams + kStretchBytes + kSquashBytes;
+    const int pgrid = (njobs + kPipeStreams - 1) / kPipeStreams;
+    if (mode == 0) bitplane_pipe_kernel<0><<<pgrid, kPipeThreads * kPipeStreams, psmem, stream>>>(d_jobs, njobs, T);
+    else bitplane_pipe_kernel<1><<<pgrid, kPipeThreads * kPipeStreams, psmem, stream>>>(d_jobs, njobs, T);
     return cudaGetLastError();
   }
   if (mode == 0) bitplane_encode_kernel<0><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);

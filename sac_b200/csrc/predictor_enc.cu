@@ -169,33 +169,52 @@ __device__ __forceinline__ void tap_load(TapRegs<R> &r, const double *fpw, const
   }
 }
 
+// The history of a stage is kept twice, back to back (2 x (N+1) entries, h[k] == h[k + N + 1]): the window of the
+// last N targets is then always contiguous at h + pos, tap i at h[pos + i], and a thread reaches its taps with
+// compile-time offsets from one pointer (the same idea as the reference's RollBuffer2, common/histbuf.h:61-88).
+//
 // phase A: chain tl accumulates taps tl, tl+128, ... in ascending order (canonical order)
 template <int R>
 __device__ __forceinline__ void tap_dot(const TapRegs<R> &r, const double *h, const double *ow, const double *opw, int N, int pos,
                                         int tl, double &ad, double &ap)
 {
-  const int cap = N + 1;
-  int hi = pos + tl;
-  if (hi >= cap) hi -= cap;
+  const double *hp = h + pos + tl;
   ad = 0.0; ap = 0.0;
 #pragma unroll
   for (int j = 0; j < R; j++) {
     if (tl + kTapThreads * j < N) {
-      const double hv = h[hi];
+      const double hv = hp[kTapThreads * j];
       ad = __fma_rn(hv, r.w[j], ad);
       ap = __fma_rn(r.pw[j], hv * hv, ap);
-      hi += kTapThreads;
-      if (hi >= cap) hi -= cap;
     }
   }
-  for (int i = tl + kTapThreads * R; i < N; i += kTapThreads) {
-    const double hv = h[hi];
+  // taps beyond the register slots (shared memory, or HBM scratch for the largest stages): four per step, all loads
+  // issued before the first fma so that their latencies overlap; the fma order per chain stays ascending in i
+  int i = tl + kTapThreads * R;
+  for (; i + 3 * kTapThreads < N; i += 4 * kTapThreads) {
+    const int o = i - kTapThreads * R;
+    const double *hq = h + pos + i;
+    const double v0 = hq[0], v1 = hq[kTapThreads], v2 = hq[2 * kTapThreads], v3 = hq[3 * kTapThreads];
+    const double w0 = ow[o], w1 = ow[o + kTapThreads], w2 = ow[o + 2 * kTapThreads], w3 = ow[o + 3 * kTapThreads];
+    const double q0 = opw[o], q1 = opw[o + kTapThreads], q2 = opw[o + 2 * kTapThreads], q3 = opw[o + 3 * kTapThreads];
+    ad = __fma_rn(v0, w0, ad); ap = __fma_rn(q0, v0 * v0, ap);
+    ad = __fma_rn(v1, w1, ad); ap = __fma_rn(q1, v1 * v1, ap);
+    ad = __fma_rn(v2, w2, ad); ap = __fma_rn(q2, v2 * v2, ap);
+    ad = __fma_rn(v3, w3, ad); ap = __fma_rn(q3, v3 * v3, ap);
+  }
+  for (; i < N; i += kTapThreads) {
+    const double hv = h[pos + i];
     const int o = i - kTapThreads * R;
     ad = __fma_rn(hv, ow[o], ad);
     ap = __fma_rn(opw[o], hv * hv, ap);
-    hi += kTapThreads;
-    if (hi >= cap) hi -= cap;
   }
+}
+
+// std::min(std::max(w, -10), 10) (ls.h:52) with one comparison: a NaN passes through exactly as in the reference
+__device__ __forceinline__ double clamp10(double w)
+{
+  const double lim = w > 0.0 ? 10.0 : -10.0;
+  return fabs(w) > 10.0 ? lim : w;
 }
 
 // phase C: w_i = clamp(fma(mutab_i, wgrad*h_i, w_i), +-10) on the pre-push window (ls.h:49-54)
@@ -203,28 +222,31 @@ template <int R>
 __device__ __forceinline__ void tap_update(TapRegs<R> &r, const double *h, double *ow, const double *omu, int N, int pos, int tl,
                                            double g)
 {
-  const int cap = N + 1;
-  int hi = pos + tl;
-  if (hi >= cap) hi -= cap;
+  const double *hp = h + pos + tl;
 #pragma unroll
   for (int j = 0; j < R; j++) {
     if (tl + kTapThreads * j < N) {
-      const double tt = g * h[hi];
-      double wn = __fma_rn(r.mu[j], tt, r.w[j]);
-      wn = dmin(dmax(wn, -10.0), 10.0);
-      r.w[j] = wn;
-      hi += kTapThreads;
-      if (hi >= cap) hi -= cap;
+      const double tt = g * hp[kTapThreads * j];
+      r.w[j] = clamp10(__fma_rn(r.mu[j], tt, r.w[j]));
     }
   }
-  for (int i = tl + kTapThreads * R; i < N; i += kTapThreads) {
+  int i = tl + kTapThreads * R;
+  for (; i + 3 * kTapThreads < N; i += 4 * kTapThreads) {
     const int o = i - kTapThreads * R;
-    const double tt = g * h[hi];
-    double wn = __fma_rn(omu[o], tt, ow[o]);
-    wn = dmin(dmax(wn, -10.0), 10.0);
-    ow[o] = wn;
-    hi += kTapThreads;
-    if (hi >= cap) hi -= cap;
+    const double *hq = h + pos + i;
+    const double v0 = hq[0], v1 = hq[kTapThreads], v2 = hq[2 * kTapThreads], v3 = hq[3 * kTapThreads];
+    double w0 = ow[o], w1 = ow[o + kTapThreads], w2 = ow[o + 2 * kTapThreads], w3 = ow[o + 3 * kTapThreads];
+    const double m0 = omu[o], m1 = omu[o + kTapThreads], m2 = omu[o + 2 * kTapThreads], m3 = omu[o + 3 * kTapThreads];
+    w0 = clamp10(__fma_rn(m0, g * v0, w0));
+    w1 = clamp10(__fma_rn(m1, g * v1, w1));
+    w2 = clamp10(__fma_rn(m2, g * v2, w2));
+    w3 = clamp10(__fma_rn(m3, g * v3, w3));
+    ow[o] = w0; ow[o + kTapThreads] = w1; ow[o + 2 * kTapThreads] = w2; ow[o + 3 * kTapThreads] = w3;
+  }
+  for (; i < N; i += kTapThreads) {
+    const int o = i - kTapThreads * R;
+    const double tt = g * h[pos + i];
+    ow[o] = clamp10(__fma_rn(omu[o], tt, ow[o]));
   }
 }
 
@@ -351,6 +373,7 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
       S.wgrad[lane] = my_mu * (bpl - pl) * my_sp / (S.spow[lane] + 1.0);
       const int np = pos == 0 ? myN : pos - 1;
       myh[np] = bpl;
+      myh[np + myN + 1] = bpl;                               // mirrored copy (see tap_dot)
       pos = np;
     }
     if (lane == 4) S.bp4 = bp[4];
@@ -858,7 +881,7 @@ __global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc
     auto take_global = [&](long long cnt) -> double * { double *r = gp; gp += cnt; return r; };
     const int regs[kStages] = {kR0, kR1, kR2, kR3};
     for (int s = 0; s < kStages; s++) { S.fpw[s] = take_global(d.vn[s]); S.fmu[s] = take_global(d.vn[s]); }
-    for (int s = kStages - 1; s >= 0; s--) S.h[s] = take(d.vn[s] + 1);
+    for (int s = kStages - 1; s >= 0; s--) S.h[s] = take(2 * (d.vn[s] + 1));
     for (int s = kStages - 1; s >= 0; s--) {
       const int ov = max(d.vn[s] - kTapThreads * regs[s], 0);
       S.ow[s] = take(ov); S.opw[s] = take(ov); S.omu[s] = take(ov);
@@ -885,10 +908,10 @@ __global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc
         const double pwv = 1.0 / c_pow((double)(1 + i), pd);  // ls.h:39
         const double muv = c_pow(md, (double)i);              // ls.h:41
         fpw[i] = pwv; fmu[i] = muv;
-        h[i] = 0.0;
+        h[i] = 0.0; h[i + N + 1] = 0.0;
         if (i >= r128) { ow[i - r128] = 0.0; opw[i - r128] = pwv; omu[i - r128] = muv; }
       }
-      if (tid == 0) h[N] = 0.0;
+      if (tid == 0) { h[N] = 0.0; h[2 * N + 1] = 0.0; }
     }
   }
   __syncthreads();
@@ -926,7 +949,7 @@ size_t predictor_ols_shared_bytes() { return (sizeof(OlsShared) + 15) & ~size_t(
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols)
 {
   long long t = 0;
-  for (int s = 0; s < kStages; s++) t += 6LL * vn[s] + 1;
+  for (int s = 0; s < kStages; s++) t += 7LL * vn[s] + 2;
   return t + 16;
 }
 // doubles of shared memory that keep every array of a chain on chip (histories + taps beyond the register slots)
@@ -934,7 +957,7 @@ long long predictor_enc_smem_doubles(const int *vn)
 {
   const int regs[kStages] = {kR0, kR1, kR2, kR3};
   long long t = 0;
-  for (int s = 0; s < kStages; s++) t += (vn[s] + 1) + 3LL * (vn[s] > kTapThreads * regs[s] ? vn[s] - kTapThreads * regs[s] : 0);
+  for (int s = 0; s < kStages; s++) t += 2 * (vn[s] + 1) + 3LL * (vn[s] > kTapThreads * regs[s] ? vn[s] - kTapThreads * regs[s] : 0);
   return t;
 }
 long long predictor_ols_scratch_doubles(int n_ols)
