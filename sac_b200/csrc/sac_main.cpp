@@ -36,7 +36,8 @@ static const char kHelp[] =
     "   --sparse-pcm       accepted (pcm modelling not implemented)\n"
     "  B200 options\n"
     "   --gpu=n            CUDA device (def=0)\n"
-    "   --frame-parallel   search all frames of the file concurrently (implies --opt-reset semantics)\n";
+    "   --frame-parallel[=1|2]  search all frames of the file concurrently (implies --opt-reset semantics):\n"
+    "                      1 = shared launches per generation, 2 = one stream and host thread per frame (default 2)\n";
 
 static std::string upper(std::string s) { for (auto &c : s) c = (char)std::toupper((unsigned char)c); return s; }
 static std::vector<std::string> split(const std::string &s, char d)
@@ -156,7 +157,7 @@ int main(int argc, const char *argv[])
       } else if (key == "--ADAPT-BLOCK") cfg.adapt_block = !(val == "NO" || val == "0");
       else if (key == "--ZERO-MEAN") cfg.zero_mean = !(val == "NO" || val == "0");
       else if (key == "--GPU") gpu = std::atoi(val.c_str());
-      else if (key == "--FRAME-PARALLEL") cfg.frame_parallel = 1;
+      else if (key == "--FRAME-PARALLEL") cfg.frame_parallel = val.empty() ? 2 : std::max(0, std::min(2, std::atoi(val.c_str())));
       else std::cerr << "warning: unknown option '" << param << "'\n";
     } else {
       if (first) { in = param; first = false; } else out = param;
