@@ -255,7 +255,7 @@ def main():
     t0 = time.perf_counter()
     run_steps(args.e2e_steps, False, args.warmup)
     barrier()
-    t_e2e = time.perf_counter() - t0
+    t_e2e = max(time.perf_counter() - t0, 1e-9)
     sampler.stop_flag = True
     # kernel-class timing of one representative generation for the roofline (CUDA events on the engine's stream)
     _, _, vdef = sb.base_profile()
@@ -267,7 +267,7 @@ def main():
     fp64_peak = eng.fp64_peak_gflops()
     t_val = shard.max_over_ranks(t_val, dev); t_e2e = shard.max_over_ranks(t_e2e, dev)
     value = FRAME * args.steps * world / t_val / 1e6
-    e2e = FRAME * args.e2e_steps * world / t_e2e / 1e6
+    e2e = FRAME * args.e2e_steps * world / t_e2e / 1e6 if args.e2e_steps > 0 else None   # 0 only for profiling runs
     # bitstream gather (outside the timed region): the only collective of the path. Unit f*world+rank = frame f of rank's stream
     gathered = None
     if world > 1:

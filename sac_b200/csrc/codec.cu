@@ -381,7 +381,7 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
     Final &F = fin[f];
     if (!F.launched || !F.eng) return SAC_OK;
     Engine *h = F.eng;
-    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    SACB_CUDA(h->wait());
     for (int c = 0; c < F.nchains; c++)
       if (h->h_flags.p[c]) { set_error("final pass: predictor state became non-finite"); return SAC_E_UNSUPPORTED; }
     // serialise (WriteEncoded / WriteBlockHeader / EncodeProfile, libsac.cpp:507-578)

@@ -161,6 +161,7 @@ int Engine::init(int dev, const Engine *parent)
     SACB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   }
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
+  SACB_CUDA(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
@@ -183,8 +184,15 @@ void Engine::destroy()
   d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release();
   if (!is_helper) bt.destroy();
   for (auto &e : ev) if (e) cudaEventDestroy(e);
+  if (ev_wait) cudaEventDestroy(ev_wait);
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr;
+}
+cudaError_t Engine::wait()
+{
+  cudaError_t e = cudaEventRecord(ev_wait, stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev_wait);
 }
 void Engine::begin_call()
 {
@@ -297,7 +305,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     SACB_CUDA(cudaMemcpyAsync(h_cost.p, d_cost.p, sizeof(double) * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(cudaEventRecord(ev[3], stream));
-    SACB_CUDA(cudaStreamSynchronize(stream));
+    SACB_CUDA(wait());
     for (int c = 0; c < nchains; c++) ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : h_cost.p[c];
     float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[2] += ms;
   } else if (cost_kind == SAC_COST_BITPLANE) {
@@ -316,14 +324,14 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     SACB_CUDA(cudaEventRecord(ev[3], stream));
     SACB_CUDA(cudaMemcpyAsync(h_sums.p, d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
-    SACB_CUDA(cudaStreamSynchronize(stream));
+    SACB_CUDA(wait());
     for (int c = 0; c < nchains; c++)
       ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : (double)h_sums.p[2 * nchains + c];
     float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[1] += ms;
   } else if (cost_kind == SAC_COST_L1 || cost_kind == SAC_COST_RMS) {
     SACB_CUDA(cudaMemcpyAsync(h_sums.p, d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
-    SACB_CUDA(cudaStreamSynchronize(stream));
+    SACB_CUDA(wait());
     for (int c = 0; c < nchains; c++) {
       const double n = (double)jobs[chain_job[c]].n;
       double v = cost_kind == SAC_COST_L1 ? h_sums.p[c] / n : std::sqrt(h_sums.p[nchains + c] / n);   // cost.h:15-41

@@ -103,6 +103,11 @@ struct Engine {           // sac_engine
   Engine *helper(int i);
   long long total_launches() const;
 
+  // waits for the stream without spinning (a blocking-sync event): the waits of this path last seconds, and several
+  // host threads (frames in flight, one rank per GPU) share the host cores
+  cudaEvent_t ev_wait = nullptr;
+  cudaError_t wait();
+
   int init(int dev, const Engine *parent = nullptr);
   void destroy();
   // residuals of every chain of `jobs` into d_resid (layout: chain c at c*stride); returns 0
