@@ -244,12 +244,14 @@ def main():
     run_steps(args.warmup, True, 0)
     barrier()
     sampler.start()
+    dd_before = eng.dedup_totals()
     l_before = eng.launches
     t0 = time.perf_counter()
     run_steps(args.steps, True, args.warmup)
     barrier()
     t_val = time.perf_counter() - t0
     l_timed = eng.launches - l_before
+    dd_timed = [a - b for a, b in zip(eng.dedup_totals(), dd_before)]
     # e2e leg: the same steps from pinned HOST planes through sac_frames_encode (H2D of the planes, D2H of the payload inside)
     barrier()
     t0 = time.perf_counter()
@@ -260,10 +262,12 @@ def main():
     # kernel-class timing of one representative generation for the roofline (CUDA events on the engine's stream)
     _, _, vdef = sb.base_profile()
     x0 = np.tile(vdef[sb.SEARCH_DIMS].astype(np.float64), (args.gen, 1))
+    prev = eng.set_dedup(0)       # the probe wants `gen` identical default chains actually evaluated
     eng.eval_population(wins[0], 220500, 441000, vdef, x0, sb.COST_BITPLANE, 4)
     barrier()
     eng.eval_population(wins[0], 220500, 441000, vdef, x0, sb.COST_BITPLANE, 4)
     ms, ln = eng.last_timing()
+    eng.set_dedup(prev)
     fp64_peak = eng.fp64_peak_gflops()
     t_val = shard.max_over_ranks(t_val, dev); t_e2e = shard.max_over_ranks(t_e2e, dev)
     value = FRAME * args.steps * world / t_val / 1e6
@@ -321,6 +325,8 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(l_timed),
+            "chains": {"requested": dd_timed[0], "evaluated": dd_timed[1], "ols_stages_evaluated": dd_timed[2],
+                       "note": "exact de-duplication: chains / OLS stages of a generation with identical inputs run once (DESIGN.md section 4.5)"},
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "note": "the path is a set of serial fp64/integer recurrences bound by instruction latency, not by HBM: "

@@ -49,6 +49,14 @@ long long sac_engine_launches(const sac_engine *);
  * [0] predictor (ols_kernel + cascade_kernel) [1] bitplane [2] entropy/other [3] ols_kernel alone; out_ms[4], out_launches[4] */
 void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_launches);
 
+/* Exact de-duplication (on by default): chains of one call whose inputs are identical -- same planes, range, k and
+ * channel parameters -- are evaluated once, and OLS stages with identical OLS parameters are computed once and shared
+ * (late in a DDS search most candidates leave one channel untouched). Results are bit-identical with and without.
+ * Returns the previous setting. sac_dedup_totals: {chains requested, chains evaluated, OLS stages evaluated} since
+ * process start. */
+int sac_engine_set_dedup(sac_engine *, int on);
+void sac_dedup_totals(long long *out3);
+
 /* measured DFMA throughput of the device (GFLOP/s, 2 flop per fma; CUDA events): the fp64 roofline denominator */
 double sac_fp64_peak_gflops(sac_engine *);
 

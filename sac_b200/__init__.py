@@ -68,6 +68,8 @@ def lib():
         L.sac_engine_launches.restype = C.c_longlong
         L.sac_engine_launches.argtypes = [C.c_void_p]
         L.sac_engine_last_timing.argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_longlong)]
+        L.sac_engine_set_dedup.argtypes = [C.c_void_p, C.c_int]
+        L.sac_dedup_totals.argtypes = [C.POINTER(C.c_longlong)]
         L.sac_window_create.restype = C.c_void_p
         L.sac_window_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(_i32p), C.c_int, _i32p]
         L.sac_window_destroy.argtypes = [C.c_void_p]
@@ -269,6 +271,16 @@ class Engine:
         _chk(lib().sac_frames_encode_resident(self.h, C.byref(cfg), nch, max_framesize, len(windows), arr, _p(mm, _i32p), _p(prof, _f32p),
                                               _p(out, _u8p), cap, C.byref(olen)), "sac_frames_encode_resident")
         return out[:olen.value].copy(), prof
+
+    def set_dedup(self, on):
+        """exact de-duplication of identical chains / OLS stages within a call; returns the previous setting"""
+        return int(lib().sac_engine_set_dedup(self.h, int(bool(on))))
+
+    @staticmethod
+    def dedup_totals():
+        out = (C.c_longlong * 3)()
+        lib().sac_dedup_totals(out)
+        return list(out)
 
     def fp64_peak_gflops(self):
         return float(lib().sac_fp64_peak_gflops(self.h))

@@ -7,11 +7,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 
 namespace sacb {
 
 static thread_local std::string g_err;
+static std::atomic<long long> g_dedup_totals[3];                    // logical chains, evaluated chains, evaluated OLS stages
 void set_error(const std::string &msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char *what)
 {
@@ -165,7 +169,9 @@ int Engine::init(int dev, const Engine *parent)
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
+  if (const char *s = std::getenv("SAC_B200_DEDUP")) dedup = std::atoi(s) != 0;
   if (parent) {
+    dedup = parent->dedup;
     enc_smem_bytes = parent->enc_smem_bytes; ols_smem_bytes = parent->ols_smem_bytes; ols_smem_cap_bytes = parent->ols_smem_cap_bytes; smem_bytes = parent->smem_bytes;
     bt = parent->bt;                                                 // shared device tables (owned by the parent)
     return SAC_OK;
@@ -199,71 +205,118 @@ void Engine::begin_call()
   for (int i = 0; i < 4; i++) { last_ms[i] = 0; last_launches[i] = 0; }
 }
 
+// Chains of one call that are bit-identical computations are evaluated once. Late in a DDS search a candidate differs
+// from the incumbent in a handful of the 56 dimensions, so most candidates of a generation leave one channel's
+// parameters -- or at least its 8 OLS parameters -- untouched: those chains (resp. their OLS stage) coincide.
+//   slot_of[c]  unique chain ("slot") of logical chain c = (job, coded channel); residuals, sums, flags are per slot
+//   OLS stage   one ols_kernel CTA per distinct (planes, range, k, OLS parameters); slots share its p_lpc plane
 int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride)
 {
   SACB_CUDA(cudaSetDevice(device));
   chain_job.clear(); chain_ch.clear();
+  slot_of.clear(); slot_rep.clear();
   size_t maxn = 0;
-  int nchains = 0;
-  for (auto &j : jobs) { nchains += j.win->nch; maxn = std::max(maxn, (size_t)j.n); }
+  int nlog = 0;
+  for (auto &j : jobs) { nlog += j.win->nch; maxn = std::max(maxn, (size_t)j.n); }
   stride = (maxn + 31) & ~size_t(31);
-  SACB_CUDA(h_descs.reserve(nchains));
-  SACB_CUDA(d_descs.reserve(nchains));
-  SACB_CUDA(d_resid.reserve(stride * nchains));
-  SACB_CUDA(d_sums.reserve((size_t)3 * nchains));
-  SACB_CUDA(d_flags.reserve((size_t)4 * nchains));
-  // scratch offsets
-  std::vector<long long> soff(nchains + 1, 0);
+  // ---- logical chains -> slots ----
   std::vector<HostParam> hps(jobs.size());
-  int c = 0;
-  for (size_t ji = 0; ji < jobs.size(); ji++) {
-    const Job &j = jobs[ji];
-    if (j.from < 0 || j.n <= 0 || j.from + j.n > j.win->numsamples) { set_error("window range outside the frame"); return SAC_E_ARG; }
-    hps[ji] = map_profile(j.profile);
-    for (int cc = 0; cc < j.win->nch; cc++, c++) soff[c + 1] = soff[c] + ((chain_scratch_doubles(hps[ji], cc, j.win->nch) + 1) & ~1LL);
-  }
-  SACB_CUDA(d_scratch.reserve((size_t)soff[nchains]));
-  std::vector<long long> ooff(nchains + 1, 0);
-  c = 0;
-  for (size_t ji = 0; ji < jobs.size(); ji++)
-    for (int cc = 0; cc < jobs[ji].win->nch; cc++, c++) ooff[c + 1] = ooff[c] + ((predictor_ols_scratch_doubles(ols_order(hps[ji], cc)) + 1) & ~1LL);
-  SACB_CUDA(d_scratch_ols.reserve((size_t)ooff[nchains]));
-  // OLS kernel shared memory for this launch: work matrix always (fast LDL path), covariance too while both stay
-  // within the cap that still leaves two CTAs per SM
-  size_t need_w = 0, need_both = 0;
-  for (size_t ji = 0; ji < jobs.size(); ji++)
-    for (int cc = 0; cc < jobs[ji].win->nch; cc++) {
-      const size_t n = (size_t)ols_order(hps[ji], cc), ld = (n + 1) | 1, mat = (n + 1) * ld * 8;
-      need_w = std::max(need_w, mat); need_both = std::max(need_both, 2 * mat);
+  std::vector<ChainDesc> descs;                                      // one per slot, inputs only
+  std::vector<int> slot_job, slot_cc;
+  {
+    std::unordered_map<std::string, int> seen;
+    for (size_t ji = 0; ji < jobs.size(); ji++) {
+      const Job &j = jobs[ji];
+      if (j.from < 0 || j.n <= 0 || j.from + j.n > j.win->numsamples) { set_error("window range outside the frame"); return SAC_E_ARG; }
+      hps[ji] = map_profile(j.profile);
+      for (int cc = 0; cc < j.win->nch; cc++) {
+        ChainDesc d;
+        const int actual = fill_chain(d, hps[ji], j.win->nch, cc, j.k, j.win->d_planes, j.from, j.n, j.win->minmax);
+        const int c = (int)chain_job.size();
+        chain_job.push_back((int)ji); chain_ch.push_back(actual);
+        int u = -1;
+        if (dedup) {
+          const std::string key(reinterpret_cast<const char *>(&d), sizeof(d));   // inputs only: outputs are still zero
+          auto it = seen.find(key);
+          if (it != seen.end()) u = it->second; else seen.emplace(key, (int)descs.size());
+        }
+        if (u < 0) { u = (int)descs.size(); descs.push_back(d); slot_rep.push_back(c); slot_job.push_back((int)ji); slot_cc.push_back(cc); }
+        slot_of.push_back(u);
+      }
     }
-  // cascade kernel: histories and overflow taps of the largest chain, capped so that two CTAs still fit an SM
-  size_t casc_need = 0;
-  for (size_t ji = 0; ji < jobs.size(); ji++)
-    for (int cc = 0; cc < jobs[ji].win->nch; cc++) casc_need = std::max(casc_need, (size_t)predictor_enc_smem_doubles(hps[ji].vn[cc]) * 8);
+  }
+  const int nu = nslots = (int)descs.size();
+  // ---- distinct OLS stages among the slots ----
+  struct OlsKey { const int32_t *own, *other; int n, lenA, lenB, lagB, minB, backB, k, pad; double lambda, nu, beta_sum, beta_pow, beta_add; };
+  std::vector<int> ols_of(nu), ols_rep;
+  {
+    std::unordered_map<std::string, int> seen;
+    for (int u = 0; u < nu; u++) {
+      const ChainDesc &d = descs[u];
+      OlsKey k;
+      std::memset(&k, 0, sizeof(k));
+      k.own = d.own; k.other = d.other; k.n = d.n; k.lenA = d.lenA; k.lenB = d.lenB; k.lagB = d.lagB; k.minB = d.minB; k.backB = d.backB; k.k = d.k;
+      k.lambda = d.lambda; k.nu = d.nu; k.beta_sum = d.beta_sum; k.beta_pow = d.beta_pow; k.beta_add = d.beta_add;
+      int v = -1;
+      if (dedup) {
+        const std::string key(reinterpret_cast<const char *>(&k), sizeof(k));
+        auto it = seen.find(key);
+        if (it != seen.end()) v = it->second; else seen.emplace(key, (int)ols_rep.size());
+      }
+      if (v < 0) { v = (int)ols_rep.size(); ols_rep.push_back(u); }
+      ols_of[u] = v;
+    }
+  }
+  const int nv = (int)ols_rep.size();
+  last_unique[0] = nlog; last_unique[1] = nu; last_unique[2] = nv;
+  g_dedup_totals[0] += nlog; g_dedup_totals[1] += nu; g_dedup_totals[2] += nv;
+  SACB_CUDA(h_descs.reserve(nu + nv));
+  SACB_CUDA(d_descs.reserve(nu + nv));
+  SACB_CUDA(d_resid.reserve(stride * nu));
+  SACB_CUDA(d_sums.reserve((size_t)3 * nu));
+  SACB_CUDA(d_flags.reserve((size_t)4 * nu));
+  SACB_CUDA(d_plpc.reserve(stride * nv));
+  // scratch offsets, shared-memory requests
+  std::vector<long long> soff(nu + 1, 0), ooff(nv + 1, 0);
+  size_t need_w = 0, need_both = 0, casc_need = 0;
+  for (int u = 0; u < nu; u++) {
+    const HostParam &hp = hps[slot_job[u]];
+    soff[u + 1] = soff[u] + ((chain_scratch_doubles(hp, slot_cc[u], jobs[slot_job[u]].win->nch) + 1) & ~1LL);
+    casc_need = std::max(casc_need, (size_t)predictor_enc_smem_doubles(hp.vn[slot_cc[u]]) * 8);
+  }
+  for (int v = 0; v < nv; v++) {
+    const int u = ols_rep[v];
+    const size_t n = (size_t)ols_order(hps[slot_job[u]], slot_cc[u]), ld = (n + 1) | 1, mat = (n + 1) * ld * 8;
+    ooff[v + 1] = ooff[v] + ((predictor_ols_scratch_doubles((int)n) + 1) & ~1LL);
+    need_w = std::max(need_w, mat); need_both = std::max(need_both, 2 * mat);
+  }
+  SACB_CUDA(d_scratch.reserve((size_t)soff[nu]));
+  SACB_CUDA(d_scratch_ols.reserve((size_t)ooff[nv]));
+  // cascade kernel: histories and overflow taps of the largest chain, capped so that two CTAs still fit an SM.
+  // OLS kernel: work matrix always (fast LDL path), covariance too while both stay within the cap
   const int casc_smem = (int)std::min<size_t>(predictor_enc_shared_bytes() + casc_need + 64, (size_t)enc_smem_bytes);
   const size_t ols_head = predictor_ols_shared_bytes();
   const size_t ols_cap = (size_t)ols_smem_cap_bytes;
   int ols_smem = (int)std::max<size_t>(std::min(ols_head + need_both, ols_cap), std::min<size_t>(ols_head + need_w, 200 * 1024));
   ols_smem = std::max(ols_smem, ols_smem_bytes);
-  SACB_CUDA(d_plpc.reserve(stride * nchains));
-  c = 0;
-  for (size_t ji = 0; ji < jobs.size(); ji++) {
-    const Job &j = jobs[ji];
-    for (int cc = 0; cc < j.win->nch; cc++, c++) {
-      ChainDesc &d = h_descs.p[c];
-      const int actual = fill_chain(d, hps[ji], j.win->nch, cc, j.k, j.win->d_planes, j.from, j.n, j.win->minmax);
-      d.resid = d_resid.p + (size_t)c * stride;
-      d.scratch = d_scratch.p + soff[c];
-      d.scratch_doubles = soff[c + 1] - soff[c];
-      d.scratch_ols = d_scratch_ols.p + ooff[c];
-      d.plpc = d_plpc.p + (size_t)c * stride;
-      d.l1sum = d_sums.p + c; d.sqsum = d_sums.p + nchains + c; d.flags = d_flags.p + c;
-      chain_job.push_back((int)ji); chain_ch.push_back(actual);
-    }
+  for (int u = 0; u < nu; u++) {
+    ChainDesc &d = h_descs.p[u];
+    d = descs[u];
+    d.resid = d_resid.p + (size_t)u * stride;
+    d.scratch = d_scratch.p + soff[u];
+    d.scratch_doubles = soff[u + 1] - soff[u];
+    d.plpc = d_plpc.p + (size_t)ols_of[u] * stride;
+    d.l1sum = d_sums.p + u; d.sqsum = d_sums.p + nu + u; d.flags = d_flags.p + u;
   }
-  SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * nchains, cudaMemcpyHostToDevice, stream));
+  for (int v = 0; v < nv; v++) {                                    // OLS descriptors follow the slot descriptors
+    ChainDesc &d = h_descs.p[nu + v];
+    d = descs[ols_rep[v]];
+    d.scratch_ols = d_scratch_ols.p + ooff[v];
+    d.plpc = d_plpc.p + (size_t)v * stride;
+  }
+  SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * (nu + nv), cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor_enc(d_descs.p, nchains, casc_smem, ols_smem, stream, ev[4]));
+  SACB_CUDA(launch_predictor_enc(d_descs.p + nu, nv, d_descs.p, nu, casc_smem, ols_smem, stream, ev[4]));
   SACB_CUDA(cudaEventRecord(ev[1], stream));
   launches += 2; last_launches[0] += 2;                             // ols_kernel + cascade_kernel
   return SAC_OK;
@@ -272,7 +325,9 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
 int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vector<int> &chain_job, const std::vector<int> &chain_ch,
                      size_t stride, double *cost)
 {
-  const int nchains = (int)chain_job.size();
+  const int nlog = (int)chain_job.size();
+  const int nchains = nslots;                                       // everything below is per slot (unique chain)
+  auto rep_job = [&](int u) -> const Job & { return jobs[chain_job[slot_rep[u]]]; };
   SACB_CUDA(h_sums.reserve((size_t)3 * nchains));
   SACB_CUDA(h_flags.reserve((size_t)2 * nchains));
   SACB_CUDA(h_cost.reserve(nchains));
@@ -284,9 +339,9 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     std::vector<int> meta(2 * nchains);
     size_t maxbins = 0;
     for (int c = 0; c < nchains; c++) {
-      const Job &j = jobs[chain_job[c]];
+      const Job &j = rep_job(c);
       meta[c] = j.n;
-      const int ch = chain_ch[c];
+      const int ch = chain_ch[slot_rep[c]];
       const long long R = (long long)j.win->minmax[2 * ch + 1] - (long long)j.win->minmax[2 * ch];
       if (cost_kind == SAC_COST_ENTROPY && R > (1 << 20)) { set_error("entropy cost: residual range above 2^20 not supported"); return SAC_E_UNSUPPORTED; }
       meta[nchains + c] = (int)std::max<long long>(R, 1);
@@ -315,7 +370,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     for (int c = 0; c < nchains; c++) {
       BpJob &b = h_bpjobs.p[c];
       std::memset(&b, 0, sizeof(b));
-      b.buf = d_resid.p + (size_t)c * stride; b.n = jobs[chain_job[c]].n; b.signed_input = 1; b.maxbpn = -1;
+      b.buf = d_resid.p + (size_t)c * stride; b.n = rep_job(c).n; b.signed_input = 1; b.maxbpn = -1;
       b.csig0 = d_csig0.p + (size_t)65536 * c; b.nbytes = d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = nullptr;
     }
     SACB_CUDA(cudaMemcpyAsync(d_bpjobs.p, h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, stream));
@@ -333,7 +388,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(wait());
     for (int c = 0; c < nchains; c++) {
-      const double n = (double)jobs[chain_job[c]].n;
+      const double n = (double)rep_job(c).n;
       double v = cost_kind == SAC_COST_L1 ? h_sums.p[c] / n : std::sqrt(h_sums.p[nchains + c] / n);   // cost.h:15-41
       ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : v;
     }
@@ -341,7 +396,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
   { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms; cudaEventElapsedTime(&ms, ev[0], ev[4]); last_ms[3] += ms; last_launches[3]++; }
   for (size_t j = 0; j < jobs.size(); j++) cost[j] = 0.0;
   // sum over channels (FrameCoder::GetCost, libsac.cpp:358-361; a two-term sum is order-independent)
-  for (int c = 0; c < nchains; c++) cost[chain_job[c]] += ccost[c];
+  for (int c = 0; c < nlog; c++) cost[chain_job[c]] += ccost[slot_of[c]];
   return SAC_OK;
 }
 
@@ -379,6 +434,20 @@ void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_
 {
   const Engine *e = reinterpret_cast<const Engine *>(h);
   for (int i = 0; i < 4; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
+}
+
+int sac_engine_set_dedup(sac_engine *h, int on)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e) return -1;
+  const int prev = e->dedup ? 1 : 0;
+  e->dedup = on != 0;
+  for (Engine *x : e->helpers) sac_engine_set_dedup(reinterpret_cast<sac_engine *>(x), on);
+  return prev;
+}
+void sac_dedup_totals(long long *out3)
+{
+  for (int i = 0; i < 3; i++) out3[i] = g_dedup_totals[i].load();
 }
 
 double sac_fp64_peak_gflops(sac_engine *h)
@@ -460,16 +529,16 @@ int sac_predict(sac_engine *h, const sac_window *wh, const float *profiles, int 
   if (rc) return rc;
   const int nchains = (int)cj.size();
   SACB_CUDA(e->h_flags.reserve((size_t)2 * nchains));
-  SACB_CUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, e->stream));
+  SACB_CUDA(cudaMemcpyAsync(e->h_flags.p, e->d_flags.p, sizeof(int) * e->nslots, cudaMemcpyDeviceToHost, e->stream));
   for (int c = 0; c < nchains; c++) {
     int32_t *dst = resid + ((size_t)cj[c] * w->nch + cc[c]) * n;
-    SACB_CUDA(cudaMemcpyAsync(dst, e->d_resid.p + (size_t)c * stride, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    SACB_CUDA(cudaMemcpyAsync(dst, e->d_resid.p + (size_t)e->slot_of[c] * stride, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
   }
   SACB_CUDA(cudaStreamSynchronize(e->stream));
   { float ms = 0; cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->last_ms[0] += ms; }
   if (flags) {
     for (int p = 0; p < P; p++) flags[p] = 0;
-    for (int c = 0; c < nchains; c++) flags[cj[c]] |= e->h_flags.p[c];
+    for (int c = 0; c < nchains; c++) flags[cj[c]] |= e->h_flags.p[e->slot_of[c]];
   }
   return SAC_OK;
 }
@@ -545,6 +614,8 @@ int sac_cost(sac_engine *h, int cost_kind, const int32_t *bufs, int count, int n
   SACB_CUDA(cudaEventRecord(e->ev[0], e->stream));
   SACB_CUDA(cudaEventRecord(e->ev[1], e->stream));
   SACB_CUDA(cudaStreamSynchronize(e->stream));
+  e->slot_of.resize(count); e->slot_rep.resize(count); e->nslots = count;
+  for (int c = 0; c < count; c++) { e->slot_of[c] = c; e->slot_rep[c] = c; }
   return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
 }
 

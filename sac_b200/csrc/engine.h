@@ -108,6 +108,12 @@ struct Engine {           // sac_engine
   cudaEvent_t ev_wait = nullptr;
   cudaError_t wait();
 
+  // chain de-duplication of the last run_predict (see engine.cu): logical chain -> slot, slot -> a representative
+  bool dedup = true;
+  std::vector<int> slot_of, slot_rep;
+  int nslots = 0;
+  long long last_unique[3] = {0, 0, 0};   // logical chains, unique chains, unique OLS stages of the last launch
+
   int init(int dev, const Engine *parent = nullptr);
   void destroy();
   // residuals of every chain of `jobs` into d_resid (layout: chain c at c*stride); returns 0
@@ -120,8 +126,8 @@ struct Engine {           // sac_engine
 
 // kernels (predictor.cu, cost.cu)
 cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream,
-                                 cudaEvent_t between = nullptr);
+cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const ChainDesc *d_descs, int nchains, int smem_bytes,
+                                 int ols_smem_bytes, cudaStream_t stream, cudaEvent_t between = nullptr);
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols);
 long long predictor_ols_scratch_doubles(int n_ols);
 size_t predictor_ols_shared_bytes();

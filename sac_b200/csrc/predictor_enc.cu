@@ -973,10 +973,10 @@ cudaError_t predictor_enc_init_attributes()
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(ols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
 }
-cudaError_t launch_predictor_enc(const ChainDesc *d_descs, int nchains, int smem_bytes, int ols_smem_bytes, cudaStream_t stream,
-                                 cudaEvent_t between)
+cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const ChainDesc *d_descs, int nchains, int smem_bytes,
+                                 int ols_smem_bytes, cudaStream_t stream, cudaEvent_t between)
 {
-  ols_kernel<<<nchains, kTeam, ols_smem_bytes, stream>>>(d_descs);
+  ols_kernel<<<nols, kTeam, ols_smem_bytes, stream>>>(d_ols_descs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess) return e;

@@ -228,3 +228,44 @@ def test_multi_frame_profile_chain_and_frame_parallel(engine):
             pos += used
         assert pos == len(rec)
     assert recs[1] == recs[2]
+
+
+def test_dedup_of_identical_chains_is_exact(engine):
+    """chains with identical inputs (a candidate that leaves one channel, or only its OLS parameters, untouched) are
+    evaluated once: costs and residuals equal those of the run without de-duplication, and fewer chains are launched"""
+    vmin, vmax, vdef = sb.base_profile()
+    pcm = synth_pcm(0.5, 2, 21).astype(np.int32)
+    planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])
+    win = engine.window(planes, mm)
+    idx = list(sb.SEARCH_DIMS)
+    base = vdef[idx].astype(np.float64)
+    X = np.tile(base, (6, 1))
+    X[1, idx.index(2)] *= 1.07           # ch0 NLMS mu only: ch1 chain identical to candidate 0, OLS stage of ch0 shared
+    X[2, idx.index(14)] *= 0.93          # ch1 NLMS mu only
+    X[3, idx.index(0)] = 0.9985          # ch0 OLS lambda: new OLS stage for ch0
+    X[4] = X[1]                          # exact duplicate candidate
+    X[5, idx.index(41)] = 3.0            # RLS order: both channels change, OLS stages shared
+    frm, n = 300, 6000
+    prev = engine.set_dedup(1)
+    t0 = engine.dedup_totals()
+    c_on = engine.eval_population(win, frm, n, vdef, X, sb.COST_BITPLANE, 4)
+    t1 = engine.dedup_totals()
+    engine.set_dedup(0)
+    c_off = engine.eval_population(win, frm, n, vdef, X, sb.COST_BITPLANE, 4)
+    t2 = engine.dedup_totals()
+    assert np.array_equal(c_on, c_off)
+    assert c_on[1] == c_on[4]
+    req, ev, ols = [a - b for a, b in zip(t1, t0)]
+    assert req == 12 and ev == 7 and ols == 3, (req, ev, ols)   # ch0 chains {0,2},{1,4},{3},{5}; ch1 chains {0,1,3,4},{2},{5}; OLS: ch0 base, ch0 lambda, ch1
+    assert [a - b for a, b in zip(t2, t1)] == [12, 12, 12]
+    # residual scatter with duplicates
+    profs = []
+    for x in X:
+        p = vdef.copy(); p[idx] = x.astype(np.float32); profs.append(p)
+    engine.set_dedup(1)
+    r_on, _ = engine.predict(win, profs, frm, n, 4)
+    engine.set_dedup(0)
+    r_off, _ = engine.predict(win, profs, frm, n, 4)
+    engine.set_dedup(prev)
+    assert np.array_equal(r_on, r_off)
+    win.close()

@@ -8,6 +8,7 @@ import oracle_lib as ol
 from synth_wav import synth_pcm
 
 eng = sb.Engine(0)
+eng.set_dedup(0)
 vmin, vmax, vdef = sb.base_profile()
 print("version", sb.lib().sac_version().decode())
 

@@ -9,6 +9,7 @@ P = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 pfrac = float(sys.argv[3]) if len(sys.argv) > 3 else 0.67
 ncheck = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 eng = sb.Engine(0); vmin, vmax, vdef = sb.base_profile()
+eng.set_dedup(0)
 pcm = synth_pcm(2, 2, 3).astype(np.int32); planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]]); win = eng.window(planes, mm)
 rng = np.random.default_rng(5)
 idx = np.array(sb.SEARCH_DIMS)

@@ -10,6 +10,7 @@ P = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
 kind = int(sys.argv[3]) if len(sys.argv) > 3 else sb.COST_BITPLANE
 eng = sb.Engine(0)
+eng.set_dedup(0)
 vmin, vmax, vdef = sb.base_profile()
 pcm = synth_pcm(2, 2, 3).astype(np.int32)
 planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])

@@ -5,6 +5,7 @@ import numpy as np, sac_b200 as sb, oracle_lib as ol
 from synth_wav import synth_pcm
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 eng = sb.Engine(0); vmin, vmax, vdef = sb.base_profile()
+eng.set_dedup(0)
 pcm = synth_pcm(2, 2, 3).astype(np.int32); planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]]); win = eng.window(planes, mm)
 for P in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "64,128,256,512,768".split(","))]:
     X = np.tile(np.asarray(vdef, np.float64)[sb.SEARCH_DIMS], (P, 1))
