@@ -691,56 +691,80 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
         inv = 1.0 / d0;
       }
       if (S.w_shared) {
-        // Fast path, work matrix in shared memory. Relative to the pivot (j,j) the element offsets of a lane never
-        // change, so a column step is a fixed 4-row x 2-column pattern per lane and 32 x 32 block: all loads are issued
-        // first (32-bit shared addresses), then the fmas, then the stores.
+        // Fast path, work matrix in shared memory, TWO columns per team barrier. Relative to the pivot (j,j) the element
+        // offsets of a lane never change, so a step is a fixed 4 x 4 register tile per lane and 32 x 64 block: all loads
+        // are issued first (32-bit shared addresses), then the fmas, then the stores. Per element the arithmetic is the
+        // canonical right-looking sequence (column j, then column j+1 with the column-j-updated values):
+        //   l_i0 = W_ij * inv_j                 u_i1 = fma(-l_i0, W_{j+1,j}, W_{i,j+1})      l_i1 = u_i1 * inv_{j+1}
+        //   W_ic = fma(-l_i1, u_c1, fma(-l_i0, W_cj, W_ic))
+        // Every lane carries the pivot chain redundantly: inv_{j+1} at the start of the step, inv_{j+2} (from the
+        // rank-2-updated element (j+2,j+2), which its owner does not store) ahead of the tile work.
         const uint32_t ldb = (uint32_t)ld * 8u;
         uint32_t pjj = (uint32_t)__cvta_generic_to_shared(W);
-        const uint32_t r0 = (uint32_t)(1 + ra) * ldb, rstep = 8u * ldb;
-        const uint32_t q0 = (uint32_t)(1 + ca) * 8u;
-        for (int j = 0; j < n && ok; j++) {
-          const int m = n - j;                                     // trailing rows rel 1..m, trailing columns rel 1..m-1
+        const uint32_t r0 = (uint32_t)(2 + ra) * ldb, rstep = 8u * ldb;
+        const uint32_t q0 = (uint32_t)(2 + ca) * 8u;
+        int j = 0;
+        while (ok && n - j >= 2) {
+          const int m = n - j;                                     // trailing rows rel 1..m (row m = b), columns rel 1..m-1
+          const double a10 = lds_f64(pjj + ldb);
+          const double l10 = a10 * inv;
+          const double d1 = __fma_rn(-l10, a10, lds_f64(pjj + ldb + 8u));
+          if (d1 < 1e-12) { ok = false; break; }
+          const double inv1 = 1.0 / d1;
           double inv_next = 0.0;
           bool ok_next = true;
-          if (m > 1) {
-            const double a = lds_f64(pjj + ldb);
-            const double dd = lds_f64(pjj + ldb + 8u);
-            const double l = a * inv;
-            const double dn = __fma_rn(-l, a, dd);
-            if (dn < 1e-12) ok_next = false;
-            inv_next = 1.0 / dn;
+          if (m > 2) {                                             // pivot of column j+2 after both updates
+            const double a0 = lds_f64(pjj + 2u * ldb), a1 = lds_f64(pjj + 2u * ldb + 8u);
+            double e = lds_f64(pjj + 2u * ldb + 16u);
+            const double l0 = a0 * inv;
+            const double u1 = __fma_rn(-l0, a10, a1);
+            const double l1 = u1 * inv1;
+            e = __fma_rn(-l0, a0, e);
+            e = __fma_rn(-l1, u1, e);
+            if (e < 1e-12) ok_next = false;
+            inv_next = 1.0 / e;
           }
-          // trailing update: per lane a 4 x 4 register tile per 32 x 64 block (8 x 16 lane grid)
-          for (int rb = 0; rb < m; rb += 32) {
-            for (int cb = 0; cb < m - 1 && cb <= rb + 31; cb += 64) {
+          for (int rb = 0; rb + 2 <= m; rb += 32) {
+            for (int cb = 0; cb + 2 <= m - 1 && cb <= rb + 31; cb += 64) {
               const uint32_t rbase = pjj + (uint32_t)rb * ldb + r0;
               const uint32_t cbase = (uint32_t)cb * 8u + q0;
-              // validity: row rel <= m, column rel <= m-1, column <= row, and not the next pivot (1,1)
-              const int rr0 = rb + 1 + ra, qq0 = cb + 1 + ca;
+              const int rr0 = rb + 2 + ra, qq0 = cb + 2 + ca;
               const int delta = qq0 - rr0;                         // element (a,b) is on/below the diagonal iff 8a - 16b >= delta
               bool rv[4], cv[4];
-              double al[4], cj[4], e[4][4];
+              double l0[4], l1[4], c0[4], c1[4], e[4][4];
 #pragma unroll
-              for (int a = 0; a < 4; a++) { rv[a] = rr0 + 8 * a <= m; al[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep) : 0.0; }
+              for (int a = 0; a < 4; a++) {
+                rv[a] = rr0 + 8 * a <= m;
+                l0[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep) : 0.0;
+                l1[a] = rv[a] ? lds_f64(rbase + (uint32_t)a * rstep + 8u) : 0.0;
+              }
 #pragma unroll
               for (int b = 0; b < 4; b++) {
                 cv[b] = qq0 + 16 * b <= m - 1;
-                cj[b] = cv[b] ? lds_f64(pjj + (uint32_t)(qq0 + 16 * b) * ldb) : 0.0;
+                const uint32_t ca_ = pjj + (uint32_t)(qq0 + 16 * b) * ldb;
+                c0[b] = cv[b] ? lds_f64(ca_) : 0.0;
+                c1[b] = cv[b] ? lds_f64(ca_ + 8u) : 0.0;
               }
               bool on[4][4];
 #pragma unroll
               for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
-                  on[a][b] = rv[a] && cv[b] && (8 * a - 16 * b >= delta) && !(a == 0 && b == 0 && rr0 == 1 && qq0 == 1);
+                  on[a][b] = rv[a] && cv[b] && (8 * a - 16 * b >= delta) && !(a == 0 && b == 0 && rr0 == 2 && qq0 == 2);
                   e[a][b] = on[a][b] ? lds_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u) : 0.0;
                 }
 #pragma unroll
               for (int a = 0; a < 4; a++) {
-                const double la = al[a] * inv;
-#pragma unroll
-                for (int b = 0; b < 4; b++) e[a][b] = __fma_rn(-la, cj[b], e[a][b]);
+                const double la0 = l0[a] * inv;
+                l1[a] = __fma_rn(-la0, a10, l1[a]) * inv1;         // l_i1
+                l0[a] = la0;
               }
+#pragma unroll
+              for (int b = 0; b < 4; b++) c1[b] = __fma_rn(-(c0[b] * inv), a10, c1[b]);   // u_c1
+#pragma unroll
+              for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) e[a][b] = __fma_rn(-l1[a], c1[b], __fma_rn(-l0[a], c0[b], e[a][b]));
 #pragma unroll
               for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -748,11 +772,24 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
                   if (on[a][b]) sts_f64(rbase + (uint32_t)a * rstep + cbase + (uint32_t)b * 128u, e[a][b]);
             }
           }
-          // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
-          for (int r = 1 + tl; r <= m; r += kTeam) sts_f64(pjj + (uint32_t)r * 8u, lds_f64(pjj + (uint32_t)r * ldb) * inv);
+          // L^T into the upper triangle: rows j and j+1 (the lower-triangle columns keep the unscaled values)
+          for (int r = 1 + tl; r <= m; r += kTeam) {
+            const double a0 = lds_f64(pjj + (uint32_t)r * ldb);
+            const double la0 = a0 * inv;
+            sts_f64(pjj + (uint32_t)r * 8u, la0);
+            if (r >= 2) {
+              const double u1 = __fma_rn(-la0, a10, lds_f64(pjj + (uint32_t)r * ldb + 8u));
+              sts_f64(pjj + ldb + (uint32_t)r * 8u, u1 * inv1);
+            }
+          }
           team_sync();
-          pjj += ldb + 8u;
+          pjj += 2u * (ldb + 8u);
+          j += 2;
           inv = inv_next; ok = ok_next;
+        }
+        if (ok && n - j == 1) {                                    // last column of an odd order: only the b row is left
+          if (tl == 0) sts_f64(pjj + 8u, lds_f64(pjj + ldb) * inv);
+          team_sync();
         }
       } else {
         for (int j = 0; j < n && ok; j++) {
