@@ -269,10 +269,16 @@ __device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int 
   for (int t = 0; t < n; t++) {
     CP(7);
     double acc[8];
+#ifdef SACB_ABLATE_TAPS
+    for (int q = 0; q < 8; q++) acc[q] = 0.0;
+    if (false)
+#endif
+    {
     tap_dot(r0, h0, ow0, opw0, N0, p0, tl, acc[0], acc[4]);
     tap_dot(r1, h1, ow1, opw1, N1, p1, tl, acc[1], acc[5]);
     tap_dot(r2, h2, ow2, opw2, N2, p2, tl, acc[2], acc[6]);
     tap_dot(r3, h3, ow3, opw3, N3, p3, tl, acc[3], acc[7]);
+    }
     CP(0);
 #pragma unroll
     for (int q = 0; q < 8; q++) acc[q] = butterfly(acc[q]);
@@ -286,10 +292,12 @@ __device__ __forceinline__ void tap_warps(EncShared &S, const ChainDesc &d, int 
     bar_sync(kBarB2, 160);
     CP(2);
     const double g0 = ldd_vol(&S.wgrad[0]), g1 = ldd_vol(&S.wgrad[1]), g2 = ldd_vol(&S.wgrad[2]), g3 = ldd_vol(&S.wgrad[3]);
+#ifndef SACB_ABLATE_TAPS
     tap_update(r0, h0, ow0, omu0, N0, p0, tl, g0);
     tap_update(r1, h1, ow1, omu1, N1, p1, tl, g1);
     tap_update(r2, h2, ow2, omu2, N2, p2, tl, g2);
     tap_update(r3, h3, ow3, omu3, N3, p3, tl, g3);
+#endif
     p0 = p0 == 0 ? N0 : p0 - 1;                              // S pushed bp[s] at this slot
     p1 = p1 == 0 ? N1 : p1 - 1;
     p2 = p2 == 0 ? N2 : p2 - 1;
@@ -383,8 +391,10 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
     CP(3);
     // ---- hand px to the bias warp ----
     if (t >= kQ) spin_until_gt(&S.q2_con, t - kQ);
+    CP(5);
     if (lane == 0) { S.q2[t & (kQ - 1)] = px; __threadfence_block(); st_vol(&S.q2_pub, t + 1); }
     // ---- mix update: LS_ADA<L1>, LS_ADA<L2> (ls.h:223-237), BlendExp (blend.h:50-90) ----
+#ifndef SACB_ABLATE_POST
     {
       if (lane < 2 * kMixN) {
         const int ex = lane / kMixN, i = lane - ex * kMixN;
@@ -409,11 +419,12 @@ __device__ __forceinline__ void scalar_warp(EncShared &S, const ChainDesc &d, in
       if (lane == 0) { S.rsum[0] = r0; S.rsum[1] = r1; S.sw[0] = w0 * inv_total; S.sw[1] = w1 * inv_total; }
       __syncwarp();
     }
+#endif
     CP(4);
   }
 #ifdef SACB_PROFILE_CASC
   if (lane == 0 && blockIdx.x < 2)
-    printf("chain %d S: clk/sample pre %.0f wait_R %.0f wait_taps %.0f crit %.0f post(mix update) %.0f\n", blockIdx.x, (double)cp[0] / n, (double)cp[1] / n, (double)cp[2] / n, (double)cp[3] / n, (double)cp[4] / n);
+    printf("chain %d S: clk/sample pre %.0f wait_R %.0f wait_taps %.0f crit %.0f wait_B(ring) %.0f post(mix update) %.0f\n", blockIdx.x, (double)cp[0] / n, (double)cp[1] / n, (double)cp[2] / n, (double)cp[3] / n, (double)cp[5] / n, (double)cp[4] / n);
 #endif
   if (lane == 0 && d.flags) *d.flags = bad ? 1 : 0;
 }
@@ -424,8 +435,15 @@ __device__ __forceinline__ void rls_warp(EncShared &S, const ChainDesc &d, int l
 {
   const int n = d.n, lm_n = d.lm_n;
   double p_rls = 0.0;
+  CP_DECL;
   for (int t = 0; t < n; t++) {
+    CP(0);
     bar_sync(kBarB3, 64);
+    CP(1);
+#ifdef SACB_ABLATE_R
+    if (t + 1 < n) { __threadfence_block(); bar_arrive(kBarB4, 64); }
+    continue;
+#endif
     const double bp4 = ldd_vol(&S.bp4);
     const double err = bp4 - p_rls;
     if (lane < lm_n) S.rph[lane] = small_dot(S.rP[lane], S.rx, lm_n);
@@ -464,7 +482,12 @@ __device__ __forceinline__ void rls_warp(EncShared &S, const ChainDesc &d, int l
       __threadfence_block();
       bar_arrive(kBarB4, 64);
     }
+    CP(2);
   }
+#ifdef SACB_PROFILE_CASC
+  if (lane == 0 && blockIdx.x < 2)
+    printf("chain %d R: clk/sample wait_S %.0f busy %.0f\n", blockIdx.x, (double)cp[1] / n, (double)cp[2] / n);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -476,14 +499,22 @@ __device__ __forceinline__ void bias_warp(EncShared &S, const ChainDesc &d, int 
   int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
   int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
   int32_t ebuf = 0;
+  CP_DECL;
   for (int t = 0; t < n; t++) {
     if ((t & 31) == 0 && t) { vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0; }
     const int32_t vali = __shfl_sync(kFull, vcur, t & 31);
     const double val = (double)vali;
+    CP(0);
     spin_until_gt(&S.q2_pub, t);
+    CP(1);
     const double px = ldd_vol(&S.q2[t & (kQ - 1)]);
     __syncwarp();
     if (lane == 0) st_vol(&S.q2_con, t + 1);
+#ifdef SACB_ABLATE_B
+    if ((t & 31) == lane) ebuf = (int32_t)px;
+    if ((t & 31) == 31 || t == n - 1) { const int base = t & ~31; if (base + lane <= t) d.resid[base + lane] = ebuf; }
+    continue;
+#endif
     // ---- bias predict (bias.h:64-126) ----
     int ctx0, ctx1, ctx2, mix_ctx;
     {
@@ -549,7 +580,12 @@ __device__ __forceinline__ void bias_warp(EncShared &S, const ChainDesc &d, int 
       }
       __syncwarp();
     }
+    CP(2);
   }
+#ifdef SACB_PROFILE_CASC
+  if (lane == 0 && blockIdx.x < 2)
+    printf("chain %d B: clk/sample top %.0f wait_S %.0f busy %.0f\n", blockIdx.x, (double)cp[0] / n, (double)cp[1] / n, (double)cp[2] / n);
+#endif
   if (lane == 0) {
     if (d.l1sum) *d.l1sum = l1;
     if (d.sqsum) *d.sqsum = sq;
