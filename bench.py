@@ -95,6 +95,9 @@ def algorithmic_flops_per_sample(profile, k):
     return f_ols(n0) + 10 * taps0 + 300, f_ols(n1) + 10 * taps1 + 300
 
 
+NFUNC_REF = 1000
+
+
 def cpu_reference_sample(frames, cores, nevals=None):
     """the reference's own objective (PredictFrame k=4 + CostBitplane per channel, libsac.cpp:389-397) on the --best
     window of frame 0, `cores` candidates concurrently (what --opt-cfg=dds,N does), plus one final pass + encode,
@@ -148,18 +151,31 @@ def cpu_reference_sample(frames, cores, nevals=None):
         for x in e:
             ol.oracle_bitplane_encode(ol.s2u(x), math=ol.MATH_LIBM)
     t_final = (time.perf_counter() - t) * 4
-    t_frame = 1000 * per_eval_wall + t_final
+    t_frame = NFUNC_REF * per_eval_wall + t_final
     return {"value": FRAME / t_frame / 1e6, "unit": "MSamples/s", "cores": cores, "kind": kind,
             "sample": "%d --best objective evaluations (441000-sample stereo window, PredictFrame k=4 + CostBitplane) run %d at a time "
-                      "(%.2f s each single-threaded, %.2f s wall per evaluation) + final pass on a quarter frame; extrapolated to 1000 "
-                      "evaluations + final pass per 882000-sample frame" % (nevals, cores, t_single, per_eval_wall),
+                      "(%.2f s each single-threaded, %.2f s wall per evaluation) + final pass on a quarter frame; extrapolated to %d "
+                      "evaluations + final pass per 882000-sample frame" % (nevals, cores, t_single, per_eval_wall, NFUNC_REF),
             "seconds_per_eval": per_eval_wall, "seconds_final": t_final}
+
+
+def workload_config(args, nfr=3):
+    """the `config` object both arms print (the reference arm times the same workload on the host cores)"""
+    return {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3+rank), --best --opt-reset; step = one 20-s frame "
+                        "(882000 sample-frames): DDS %d evaluations in generations of %d (--opt-cfg=dds,%d: run_mt/SSC1), window 441000, "
+                        "CostBitplane, k=4; final pass k=1 + bitplane payload; %d frames in flight per GPU (one stream each)"
+                        % (args.nfunc, args.gen, args.gen, args.inflight),
+            "generation": args.gen, "nfunc": args.nfunc, "frames": nfr, "frames_in_flight": args.inflight, "e2e_steps": args.e2e_steps,
+            "l2": "inputs per step (7 MB planes + 3.5 MB of p_lpc and 1.7 MB of residuals per chain, 256 chains per generation) "
+                  "exceed the 126 MB L2; no flush"}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    global NFUNC_REF
+    NFUNC_REF = args.nfunc
     cores = os.cpu_count() or 1
     frames = stream_frames(20, 3)
     vals = []
@@ -176,15 +192,16 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": FRAME / v / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV, --best; step = one 882000-sample frame "
-                                   "(bounded sample, extrapolated linearly in the DDS evaluation count)", "nfunc": 1000, "window": 441000},
+            "config": workload_config(args),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
 def main():
+    global NFUNC_REF
     args = parse()
+    NFUNC_REF = args.nfunc
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -315,13 +332,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "MSamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_val / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3+rank), --best --opt-reset; step = one 20-s frame "
-                                   "(882000 sample-frames): DDS %d evaluations in generations of %d (--opt-cfg=dds,%d: run_mt/SSC1), window 441000, "
-                                   "CostBitplane, k=4; final pass k=1 + bitplane payload; %d frames in flight per GPU (one stream each)"
-                                   % (args.nfunc, args.gen, args.gen, args.inflight),
-                       "generation": args.gen, "nfunc": args.nfunc, "frames": nfr, "frames_in_flight": args.inflight, "e2e_steps": args.e2e_steps,
-                       "l2": "inputs per step (7 MB planes + 3.5 MB of p_lpc and 1.7 MB of residuals per chain, 256 chains per generation) "
-                             "exceed the 126 MB L2; no flush"},
+            "config": workload_config(args, nfr),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(l_timed),
