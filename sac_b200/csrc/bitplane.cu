@@ -6,13 +6,13 @@
 // reproduced exactly; tests compare payload bytes with the reference's own BitplaneCoder.
 //
 // Encoder structure ("contexts are a pure function of the residual array"): per plane the
-// stream is walked in chunks of 32 samples. All 32 lanes first compute, in parallel, everything about "their"
-// sample that does not depend on adaptive state -- windowed magnitude mean (prefix sums), Laplace estimate (table),
-// significance patterns and counts (ballots), refinement contexts -- and prefetch the one large-table counter
-// (csig0, 64K entries, HBM/L2). Then the warp walks the 32 decisions in order, executing the adaptive chain
-// (counters, mixers, SSE, coder) uniformly; the per-sample records come from the owning lane by shuffle.
+// stream is walked in chunks of 32 samples. All 32 lanes of the first pipeline warp compute, in parallel, everything
+// about "their" sample that does not depend on adaptive state -- windowed magnitude mean (prefix sums), Laplace
+// estimate (table), significance patterns and counts (ballots), refinement contexts -- and prefetch the one
+// large-table counter (csig0, 64K entries, HBM/L2). The adaptive chain of the 32 decisions then runs as a pipeline
+// of four warps (counters -> mixer -> SSE -> final mixer + coder), see bitplane_pipe_kernel.
 // The decoder cannot look ahead (contexts depend on bits decoded in the current plane) and evaluates each
-// decision cooperatively across the warp instead.
+// decision cooperatively across one warp instead.
 #include "bitplane.h"
 #include "sac_canon_math.h"
 #include <cuda_runtime.h>
@@ -261,167 +261,6 @@ __device__ __forceinline__ Tables stage_tables(const Tables &G, unsigned char *s
   T.stretch = reinterpret_cast<const int16_t *>(smem);
   T.squash = sq;
   return T;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// encoder / byte counter. One warp per job.
-template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_encode_kernel(const BpJob *__restrict__ jobs, int njobs, Tables TG)
-{
-  extern __shared__ __align__(16) unsigned char bp_smem[];
-  const Tables T = stage_tables(TG, bp_smem);
-  BpState *states = reinterpret_cast<BpState *>(bp_smem + kStretchBytes + kSquashBytes);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int job = blockIdx.x * kWarpsPerCta + wib;
-  if (job >= njobs) return;
-  const BpJob J = jobs[job];
-  BpState &S = states[wib];
-  const int n = J.n;
-  int32_t *u = J.buf;
-
-  // ---- S2U map (utils.h:248-253) and maxbpn (libsac.cpp:429-441, cost.h:150-158) ----
-  uint32_t vmax = 0;
-  if (J.signed_input) {
-    for (int i = lane; i < n; i += 32) {
-      const int32_t v = u[i];
-      const int32_t m = v < 0 ? 2 * (-v) : (v > 0 ? 2 * v - 1 : 0);
-      u[i] = m;
-      vmax = max(vmax, (uint32_t)m);
-    }
-  } else {
-    for (int i = lane; i < n; i += 32) vmax = max(vmax, (uint32_t)u[i]);
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) vmax = max(vmax, __shfl_xor_sync(kFull, vmax, o));
-  const int maxbpn = J.maxbpn >= 0 ? J.maxbpn : max(topbit(vmax), 0);
-  init_state(S, J.csig0, lane);
-
-  Coder rc;
-  rc.range = 0xFFFFFFFFu; rc.ffnum = 0; rc.cache = 0; rc.lowc = 0; rc.nbytes = 0; rc.out = J.out;
-  const int nchunks = (n + 31) >> 5;
-
-  for (int bpn = maxbpn; bpn >= 0; bpn--) {
-    const int shA = bpn + 1, shB = max(bpn, 1);
-    const uint32_t himask = ~((2u << bpn) - 1u);
-    // sliding registers: prev / cur / next chunk
-    uint32_t u_prev = 0, u_cur = 0, u_next = lane < n ? (uint32_t)u[lane] : 0u;
-    uint32_t pre_cur = 0, tot_cur = 0, hi_cur = 0, suf_prev = 0;
-    uint32_t pre_next, tot_next;
-    {
-      const uint32_t h = u_next & himask;
-      pre_next = scan_incl(h, lane);
-      tot_next = __shfl_sync(kFull, pre_next, 31);
-    }
-    uint32_t A_prev = 0, A_cur = 0, A_next = __ballot_sync(kFull, (u_next >> shA) != 0);
-    uint32_t B_prev = 0, B_cur = 0;
-    uint32_t K_prev = 0, K_cur = 0;                                // bit bpn of each sample
-
-    for (int c = 0; c < nchunks; c++) {
-      const int base = c << 5, s = base + lane;
-      // ---- advance the window ----
-      suf_prev = tot_cur - pre_cur + hi_cur;
-      u_prev = u_cur; u_cur = u_next;
-      pre_cur = pre_next; tot_cur = tot_next; hi_cur = u_cur & himask;
-      A_prev = A_cur; A_cur = A_next; B_prev = B_cur; K_prev = K_cur;
-      {
-        const int sn = s + 32;
-        u_next = sn < n ? (uint32_t)u[sn] : 0u;
-        const uint32_t h = u_next & himask;
-        pre_next = scan_incl(h, lane);
-        tot_next = __shfl_sync(kFull, pre_next, 31);
-        A_next = __ballot_sync(kFull, (u_next >> shA) != 0);
-      }
-      B_cur = __ballot_sync(kFull, (u_cur >> shB) != 0);
-      K_cur = __ballot_sync(kFull, ((u_cur >> bpn) & 1u) != 0);
-
-      // ---- per-lane context record for sample s ----
-      const unsigned long long AL = ((unsigned long long)A_cur << 32) | A_prev;
-      const unsigned long long BL = ((unsigned long long)B_cur << 32) | B_prev;
-      const unsigned long long KL = ((unsigned long long)K_cur << 32) | K_prev;
-      const unsigned long long AR = ((unsigned long long)A_next << 32) | A_cur;
-      const uint32_t a_left = (uint32_t)(AL >> lane), b_left = (uint32_t)(BL >> lane), k_left = (uint32_t)(KL >> lane);
-      const uint32_t a_right = (uint32_t)(AR >> (lane + 1));       // bit i <-> sample s+1+i
-      // right counts exclude the stream's last sample (vle.cpp:152: sample+i < numsamples-1)
-      uint32_t a_right_cnt = a_right;
-      { const int dl = (n - 1) - (s + 1); if (dl >= 0 && dl < 32) a_right_cnt &= ~(1u << dl); }
-      auto leftbit = [&](uint32_t wbits, int dd) { return (int)((wbits >> (32 - dd)) & 1u); };
-      auto rightbit = [&](uint32_t wbits, int dd) { return (int)((wbits >> (dd - 1)) & 1u); };
-
-      const int selfA = (int)((A_cur >> lane) & 1u);
-      const int bit = (int)((u_cur >> bpn) & 1u);
-      // windowed mean of the already-known magnitude bits (vle.cpp:54-68)
-      const uint32_t nsum = suf_prev + tot_cur + pre_next + ((uint32_t)__popc(k_left) << bpn);
-      const int nidx = min(s + 32, n - 1) - max(s - 32, 0) + 1;
-      const uint32_t avg = s < n ? (nsum + (uint32_t)(nidx - 1)) / (uint32_t)nidx : 0u;
-      const int pe = laplace_p(T, avg, bpn);
-      // neighbours' raw values
-      auto nb = [&](int dd) -> uint32_t {                          // value of sample s+dd, |dd| <= 4
-        const int sl = lane + dd;
-        const uint32_t vc = __shfl_sync(kFull, u_cur, sl & 31);
-        const uint32_t vp = __shfl_sync(kFull, u_prev, sl & 31);
-        const uint32_t vn = __shfl_sync(kFull, u_next, sl & 31);
-        return sl < 0 ? vp : (sl > 31 ? vn : vc);
-      };
-      const uint32_t l1 = nb(-1), l2 = nb(-2), l3 = nb(-3), l4 = nb(-4);
-      const uint32_t r1 = nb(1), r2 = nb(2), r3 = nb(3), r4 = nb(4);
-      uint32_t rec0, rec1, cs_val = 0;
-      const int sse2 = 32 + selfA + (leftbit(b_left, 1) << 1) + (rightbit(a_right, 1) << 2) + (leftbit(b_left, 2) << 3) +
-                       (rightbit(a_right, 2) << 4) + (leftbit(b_left, 3) << 5) + (rightbit(a_right, 3) << 6);
-      rec0 = (uint32_t)pe | ((uint32_t)bit << 15) | ((uint32_t)selfA << 16) | ((uint32_t)sse2 << 17);
-      if (selfA) {
-        const int b0 = (int)(u_cur >> (bpn + 1)), b1 = (int)(l1 >> bpn), b2 = (int)(r1 >> (bpn + 1));
-        const int b3 = (int)(l2 >> bpn), b4 = (int)(r2 >> (bpn + 1));
-        const int c0 = (b0 << 1) < b1, c1 = b0 < b2, c2 = (b0 << 1) < b3, c3 = b0 < b4;
-        const int x0 = b0 << 1, x1 = b1, x2 = b2 << 1, x3 = b3, x4 = b4 << 1;
-        const int xm = (x0 + x1 + x2 + x3 + x4) / 5;
-        const int d0 = x0 > xm, d1 = x1 > xm;
-        const int cc1 = (b0 & 15) + ((b1 & 15) << 4);
-        const int cc2 = (c0 + (c1 << 1) + (c2 << 2) + (c3 << 3)) + (d0 << 4) + (d1 << 5);
-        auto msbL = [&](uint32_t v) { return (v >> shB) != 0 ? topbit(v) : 0; };
-        auto msbR = [&](uint32_t v) { return (v >> shA) != 0 ? topbit(v) : 0; };
-        const int cc3 = msbL(l1) + msbR(r1) + msbL(l2) + msbR(r2) + msbL(l3) + msbR(r3) + msbL(l4) + msbR(r4);
-        const int pctx = ((((pe >> 12) << 1) + d0) << 1) + (b0 & 1);
-        rec1 = (uint32_t)topbit(u_cur) | ((uint32_t)cc1 << 5) | ((uint32_t)cc2 << 13) | ((uint32_t)cc3 << 19) | ((uint32_t)pctx << 27);
-      } else {
-        int ctx1 = 0;
-#pragma unroll
-        for (int dd = 1; dd <= 8; dd++) ctx1 |= (leftbit(b_left, dd) << (2 * dd - 2)) | (rightbit(a_right, dd) << (2 * dd - 1));
-        const int n1 = __popc(b_left) + __popc(a_right_cnt);
-        const int n2 = __popc(a_left) + __popc(a_right_cnt);
-        int st4 = 0;
-#pragma unroll
-        for (int dd = 1; dd <= 4; dd++) st4 |= ((s - dd >= 0 && !leftbit(a_left, dd)) ? 1 : 0) << (dd - 1);
-        const int mixctx = (st4 << 3) + (min(n1, 3) << 1) + (n2 > 0 ? 1 : 0);
-        rec1 = (uint32_t)ctx1 | ((uint32_t)n2 << 16) | ((uint32_t)mixctx << 23);
-        if (s < n) cs_val = J.csig0[ctx1];
-      }
-
-      // ---- the serial chain over this chunk ----
-      const int cnt = min(32, n - base);
-      for (int j = 0; j < cnt; j++) {
-        const uint32_t w0 = __shfl_sync(kFull, rec0, j), w1 = __shfl_sync(kFull, rec1, j);
-        uint32_t cs = __shfl_sync(kFull, cs_val, j);
-        Decision d;
-        d.pe = (int)(w0 & 0x7fff); d.bit = (int)((w0 >> 15) & 1); d.is_ref = (int)((w0 >> 16) & 1); d.sse2 = (int)((w0 >> 17) & 0xff);
-        d.ctx1 = (int)(w1 & 0xffff); d.n2 = (int)((w1 >> 16) & 0x7f); d.mixctx = (int)((w1 >> 23) & 0x7f);
-        d.tb = (int)(w1 & 31); d.c1 = (int)((w1 >> 5) & 0xff); d.c2 = (int)((w1 >> 13) & 0x3f); d.c3 = (int)((w1 >> 19) & 0xff); d.pctx = (int)(w1 >> 27);
-        const uint32_t cs_old = cs;
-        model_step(S, T, d, bpn, cs, [&](int p) { rc_encode<MODE>(rc, p, d.bit, lane); return d.bit; });
-        if (!d.is_ref) {
-          if (lane == 0) J.csig0[d.ctx1] = cs;
-          // keep the prefetched copies of later samples coherent
-          if (!selfA && lane > j && (int)(rec1 & 0xffff) == d.ctx1) cs_val = cs;
-          (void)cs_old;
-        }
-      }
-      __syncwarp();
-    }
-  }
-  for (int i = 0; i < 5; i++) shift_low<MODE>(rc, lane);           // RangeCoderSH::Stop (range.cpp:61-64)
-  if (lane == 0) {
-    if (J.nbytes) *J.nbytes = rc.nbytes;
-    if (J.maxbpn_out) *J.maxbpn_out = maxbpn;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -966,8 +805,6 @@ cudaError_t bitplane_init_attributes()
   const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
   const int psmem = (int)sizeof(PipeShared) * kPipeStreams + kStretchBytes + kSquashBytes;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(bitplane_encode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(bitplane_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(bitplane_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(bitplane_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
@@ -978,17 +815,14 @@ cudaError_t launch_bitplane(const BitplaneTables &bt, const BpJob *d_jobs, int n
   Tables T{bt.d_stretch, bt.d_squash, bt.d_laplace, bt.lap_bits};
   const int grid = (njobs + kWarpsPerCta - 1) / kWarpsPerCta;
   const int smem = (int)(sizeof(BpState) * kWarpsPerCta) + kStretchBytes + kSquashBytes;
-  static const bool use_pipe = !(getenv("SAC_B200_BP_PIPE") && atoi(getenv("SAC_B200_BP_PIPE")) == 0);
-  if (mode != 2 && use_pipe) {
+  if (mode != 2) {
     const int psmem = (int)sizeof(PipeShared) * kPipeStreams + kStretchBytes + kSquashBytes;
     const int pgrid = (njobs + kPipeStreams - 1) / kPipeStreams;
     if (mode == 0) bitplane_pipe_kernel<0><<<pgrid, kPipeThreads * kPipeStreams, psmem, stream>>>(d_jobs, njobs, T);
     else bitplane_pipe_kernel<1><<<pgrid, kPipeThreads * kPipeStreams, psmem, stream>>>(d_jobs, njobs, T);
     return cudaGetLastError();
   }
-  if (mode == 0) bitplane_encode_kernel<0><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);
-  else if (mode == 1) bitplane_encode_kernel<1><<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);
-  else bitplane_decode_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);
+  bitplane_decode_kernel<<<grid, kWarpsPerCta * 32, smem, stream>>>(d_jobs, njobs, T);
   return cudaGetLastError();
 }
 

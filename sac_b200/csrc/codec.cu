@@ -600,7 +600,7 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
   }
   SACB_CUDA(cudaMemcpyAsync(e->d_descs.p, e->h_descs.p, sizeof(ChainDesc) * nch, cudaMemcpyHostToDevice, e->stream));
   SACB_CUDA(cudaEventRecord(e->ev[0], e->stream));
-  SACB_CUDA(launch_predictor(e->d_descs.p, nch, e->smem_bytes, true, e->stream));
+  SACB_CUDA(launch_predictor_decode(e->d_descs.p, nch, e->smem_bytes, e->stream));
   SACB_CUDA(cudaEventRecord(e->ev[1], e->stream));
   e->launches++; e->last_launches[0]++;
   for (int ch = 0; ch < nch; ch++) {

@@ -125,7 +125,7 @@ struct Engine {           // sac_engine
 };
 
 // kernels (predictor.cu, cost.cu)
-cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream);
+cudaError_t launch_predictor_decode(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream);
 cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const ChainDesc *d_descs, int nchains, int smem_bytes,
                                  int ols_smem_bytes, cudaStream_t stream, cudaEvent_t between = nullptr);
 long long predictor_enc_scratch_doubles(const int *vn, int n_ols);

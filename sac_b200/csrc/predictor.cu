@@ -1,5 +1,6 @@
-// predictor.cu -- the per-sample fp64 recurrence (OLS -> 4-stage NLMS cascade + RLS -> 2-expert mix -> bias) as a
-// warp-specialised sm_100a kernel. One CTA per chain (candidate x coded channel), 160 threads:
+// predictor.cu -- DECODE direction of the per-sample fp64 recurrence (OLS -> 4-stage NLMS cascade + RLS -> 2-expert
+// mix -> bias): in the decoder every stage needs the sample just reconstructed, so the recurrence cannot be split
+// the way predictor_enc.cu splits the encoder's. One CTA per chain (coded channel), 160 threads:
 //
 //   warp 0      "scalar warp": OLS (regressor, dot, covariance, LDL^T), stage targets, mix/blend, RLS, bias,
 //               round/clamp/residual -- everything that is O(n_ols^2) or O(1) per sample
@@ -557,14 +558,12 @@ size_t predictor_scalar_bytes() { return (sizeof(Scalar) + 15) & ~size_t(15); }
 
 cudaError_t predictor_init_attributes()
 {
-  cudaError_t e = cudaFuncSetAttribute(predictor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(predictor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+  return cudaFuncSetAttribute(predictor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
 }
-cudaError_t launch_predictor(const ChainDesc *d_descs, int nchains, int smem_bytes, bool decode, cudaStream_t stream)
+// decode direction only: the encode direction is predictor_enc.cu (ols_kernel + cascade_kernel)
+cudaError_t launch_predictor_decode(const ChainDesc *d_descs, int nchains, int smem_bytes, cudaStream_t stream)
 {
-  auto kern = decode ? predictor_kernel<true> : predictor_kernel<false>;
-  kern<<<nchains, kBlockThreads, smem_bytes, stream>>>(d_descs);
+  predictor_kernel<true><<<nchains, kBlockThreads, smem_bytes, stream>>>(d_descs);
   return cudaGetLastError();
 }
 

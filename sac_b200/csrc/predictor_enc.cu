@@ -837,46 +837,8 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
           team_sync();
         }
       } else {
-        for (int j = 0; j < n && ok; j++) {
-          double inv_next = 0.0;
-          bool ok_next = true;
-          if (j + 1 < n) {
-            const double a = W[(j + 1) * ld + j];
-            const double l = a * inv;
-            const double dn = __fma_rn(-l, a, W[(j + 1) * ld + j + 1]);
-            if (dn < 1e-12) ok_next = false;
-            inv_next = 1.0 / dn;
-          }
-          // trailing update, 2 rows x 2 columns per lane and step: loads, fmas, stores
-          for (int cb = j + 1 + ca; cb < n; cb += 32) {
-            const int c1 = cb + 16;
-            const double cj0 = W[cb * ld + j];
-            const double cj1 = c1 < n ? W[c1 * ld + j] : 0.0;
-            int i0 = j + 1 + ra;
-            if (i0 < cb) i0 += ((cb - i0 + 7) >> 3) << 3;      // rows at or below the tile's first column (c <= i)
-            for (; i0 <= n; i0 += 16) {
-              const int i1 = i0 + 8;
-              const bool r1 = i1 <= n;
-              const double a0 = W[i0 * ld + j], a1 = r1 ? W[i1 * ld + j] : 0.0;
-              const int m0 = min(i0, n - 1), m1 = min(i1, n - 1);
-              const bool s00 = cb <= m0 && !(i0 == j + 1 && cb == j + 1), s01 = c1 <= m0;
-              const bool s10 = r1 && cb <= m1, s11 = r1 && c1 <= m1;
-              double e00 = s00 ? W[i0 * ld + cb] : 0.0, e01 = s01 ? W[i0 * ld + c1] : 0.0;
-              double e10 = s10 ? W[i1 * ld + cb] : 0.0, e11 = s11 ? W[i1 * ld + c1] : 0.0;
-              const double l0 = a0 * inv, l1 = a1 * inv;
-              e00 = __fma_rn(-l0, cj0, e00); e01 = __fma_rn(-l0, cj1, e01);
-              e10 = __fma_rn(-l1, cj0, e10); e11 = __fma_rn(-l1, cj1, e11);
-              if (s00) W[i0 * ld + cb] = e00;
-              if (s01) W[i0 * ld + c1] = e01;
-              if (s10) W[i1 * ld + cb] = e10;
-              if (s11) W[i1 * ld + c1] = e11;
-            }
-          }
-          // L^T into the upper triangle: column j scaled (the lower-triangle column keeps the unscaled values)
-          for (int i = j + 1 + tl; i <= n; i += kTeam) W[j * ld + i] = W[i * ld + j] * inv;
-          team_sync();
-          inv = inv_next; ok = ok_next;
-        }
+        // the host always sizes the launch so that the work matrix fits shared memory (n <= 96: 75 KB)
+        __trap();
       }
       if (ok && tw == 0) {
         // back substitution L^T w = z (z = row n of L), columns in descending order, one fma per element
