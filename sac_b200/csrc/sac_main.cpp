@@ -63,7 +63,7 @@ static std::string time_str(long long numsamples, long long sr)
 }
 static void print_md5(const uint8_t d[16]) { for (int i = 0; i < 16; i++) std::printf("%x", (int)d[i]); }   // cmdline.cpp:313 (no zero padding)
 
-static int list_file(const std::string &path, bool full)
+static int list_file(const std::string &path, bool full, int mt_mode)
 {
   std::ifstream f(path, std::ios::binary);
   if (!f) { std::cout << "could not open\n"; return 1; }
@@ -77,7 +77,7 @@ static int list_file(const std::string &path, bool full)
   const double bps = (b.size() * 8.0) / ((double)ns * nch);
   std::printf("  WAVE  Codec: PCM (%d kbps)\n  %dHz %d Bit  %s\n  %u Samples [%s]\n", (int)std::round((sr * nch * bps) / 1000), sr, bits,
               nch == 1 ? "Mono" : "Stereo", ns, time_str(ns, sr).c_str());
-  std::printf("  Profile: %ds\n  Ratio:   %.3f bps\n\n  Audio MD5: ", fl, bps);
+  std::printf("  Profile: mt%d %ds\n  Ratio:   %.3f bps\n\n  Audio MD5: ", mt_mode, fl, bps);   // cmdline.cpp:307-311
   size_t pos = 22 + md;
   print_md5(&b[pos]);
   std::printf("\n");
@@ -111,6 +111,7 @@ int main(int argc, const char *argv[])
   std::string in, out;
   bool first = true;
   int gpu = 0;
+  int mt_mode = 2;                                                    // tsac_cfg default (libsac.h:19-44); listings echo it
   for (int k = 1; k < argc; k++) {
     const std::string param = argv[k];
     const std::string up = upper(param);
@@ -145,7 +146,7 @@ int main(int argc, const char *argv[])
           } else std::cerr << "unknown option: " << val << '\n';
         }
       } else if (key == "--FRAMELEN") { if (val.size()) cfg.max_framelen = std::max(0, std::atoi(val.c_str())); }
-      else if (key == "--MT-MODE") {}
+      else if (key == "--MT-MODE") { if (val.size()) mt_mode = std::max(0, std::min(2, std::atoi(val.c_str()))); }   // cmdline.cpp:185-187 (only echoed)
       else if (key == "--SPARSE-PCM") cfg.sparse_pcm = !(val == "NO" || val == "0");
       else if (key == "--STEREO-MS") {}
       else if (key == "--OPT-RESET") cfg.reset = 1;
@@ -165,7 +166,9 @@ int main(int argc, const char *argv[])
   }
   if (mode == LIST || mode == LISTFULL) {
     std::cout << "Open: '" << in << "': ";
-    return list_file(in, mode == LISTFULL);
+    const int rc = list_file(in, mode == LISTFULL, mt_mode);
+    std::printf("\n  Time:    [00:00:00]\n");                          // cmdline.cpp:355-356
+    return rc;
   }
   sac_engine *eng = sac_engine_create(gpu);
   if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }

@@ -89,3 +89,18 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", sb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_cli_listing_of_a_reference_file_matches_the_reference_cli():
+    """container fidelity: `sac --list/--listfull` on a .sac written by the UNMODIFIED reference CLI
+    prints exactly what the reference prints for it (header fields, metadata size, MD5 formatting quirk, per-frame block
+    headers, coefficient/blocks byte counts). Fixture and expected text: tests/golden/make_cli_fixture.sh. No GPU needed."""
+    import subprocess
+    gold = os.path.join(ROOT, "tests", "golden")
+    cli = os.path.join(ROOT, "sac_b200", "sac")
+    assert os.path.exists(cli), "build the CLI first (make -C sac_b200/csrc)"
+    for flag, ext in (("--listfull", "listfull"), ("--list", "list")):
+        out = subprocess.run([cli, flag, "ref_stereo_quarter_normal.sac"], cwd=gold, capture_output=True, text=True, timeout=60).stdout
+        got = out[out.index("Open:"):].splitlines()
+        want = open(os.path.join(gold, "ref_stereo_quarter_normal.%s.txt" % ext)).read().splitlines()
+        assert got == want, (flag, got, want)
