@@ -102,8 +102,13 @@ int sac_eval_jobs(sac_engine *, int njobs, const sac_window *const *wins, const 
 typedef int (*sac_eval_fn)(const double *X, int P, int D, double *cost, void *user);
 double sac_dds_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
                    double sigma_init, sac_eval_fn eval, void *user, double *xbest);
+/* OptDE::run (src/opt/de.cpp:80-172; NP = 30, current-to-pbest/1/bin, adaptive CR and F) over the same evaluator seam:
+ * the start vector, then the 29 initial samples, then generations of up to 30 trial vectors */
+double sac_de_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
+                  sac_eval_fn eval, void *user, double *xbest);
 
 /* ---- frame coding ------------------------------------------------------------------------------------------------ */
+enum { SAC_SEARCH_DDS = 0, SAC_SEARCH_DE = 1, SAC_SEARCH_CMA = 2 };   /* FrameCoder::SearchMethod (src/libsac/libsac.h) */
 typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac/libsac.h:19-44) */
   int optimize;                 /* 0 = --normal */
   double fraction;              /* window fraction of max_framesize */
@@ -120,6 +125,7 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
   int frame_parallel;           /* B200 extension (implies --opt-reset semantics): 1 = all frames of a call share each generation's launches,
                                    2 = every frame runs on its own stream / host thread, all concurrently on the GPU */
   int verbose;
+  int search;                   /* SAC_SEARCH_*: --opt-cfg=dds|de (src/cmdline.cpp:195-206); cma is not built */
 } sac_cfg;
 void sac_cfg_default(sac_cfg *);
 /* presets of src/cmdline.cpp:127-156: "normal","high","veryhigh","extrahigh","best","insane" */

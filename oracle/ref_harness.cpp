@@ -38,6 +38,7 @@
 #include "libsac/cost.h"
 #include "libsac/vle.h"
 #include "opt/dds.h"
+#include "opt/de.h"
 #include "opt/ssc.h"
 #undef private
 #undef protected
@@ -263,6 +264,20 @@ void ref_dds_candidates(int ndim, const double *xmin, const double *xmax, const 
     vec1D cand = dds.generate_candidate(xv, nfunc0 + c, sigma);
     std::copy_n(cand.begin(), ndim, out + (size_t)c * ndim);
   }
+}
+// ---- DE (src/opt/de.cpp), one evaluation thread so that the trace is in generation order --------------------------
+double ref_de_run(int ndim, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
+                  ref_cost_cb cb, void *user, double *xbest)
+{
+  Opt::box_const pb(ndim);
+  for (int i = 0; i < ndim; i++) { pb[i].xmin = xmin[i]; pb[i].xmax = xmax[i]; }
+  OptDE::DECfg cfg;                              // NP 30, CR .5, F .5, c .1, CURPBEST, INIT_NORM, pbest .1 (de.h:18-31)
+  cfg.nfunc_max = nfunc_max; cfg.num_threads = 1; cfg.sigma_init = sigma_init;
+  OptDE de(cfg, pb, false);
+  vec1D xs(xstart, xstart + ndim);
+  Opt::ppoint r = de.run([&](const vec1D &x) { return cb(x.data(), ndim, user); }, xs);
+  std::copy_n(r.second.begin(), ndim, xbest);
+  return r.first;
 }
 double ref_ssc0_trace(const int *succ, int n, double sigma, double *out)
 {

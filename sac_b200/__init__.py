@@ -18,6 +18,7 @@ CLI_PATH = os.path.join(_HERE, "sac")
 PROFILE_SIZE = 58
 SEARCH_DIMS = [i for i in range(58) if i not in (56, 57)]
 COST_L1, COST_RMS, COST_ENTROPY, COST_GOLOMB, COST_BITPLANE = range(5)
+SEARCH_DDS, SEARCH_DE, SEARCH_CMA = range(3)
 
 _i32p = C.POINTER(C.c_int32)
 _f32p = C.POINTER(C.c_float)
@@ -36,7 +37,7 @@ class Cfg(C.Structure):
     _fields_ = [("optimize", C.c_int), ("fraction", C.c_double), ("maxnfunc", C.c_int), ("num_threads", C.c_int),
                 ("sigma", C.c_double), ("optk", C.c_int), ("cost_kind", C.c_int), ("reset", C.c_int), ("zero_mean", C.c_int),
                 ("sparse_pcm", C.c_int), ("max_framelen", C.c_int), ("adapt_block", C.c_int), ("frame_parallel", C.c_int),
-                ("verbose", C.c_int)]
+                ("verbose", C.c_int), ("search", C.c_int)]
 
 
 class FileStats(C.Structure):
@@ -83,6 +84,8 @@ def lib():
                                     C.c_int, C.c_int, _f64p]
         L.sac_dds_run.restype = C.c_double
         L.sac_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
+        L.sac_de_run.restype = C.c_double
+        L.sac_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
         L.sac_cfg_default.argtypes = [C.POINTER(Cfg)]
         L.sac_cfg_preset.argtypes = [C.POINTER(Cfg), C.c_char_p]
         L.sac_frames_encode.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_int, C.c_int, C.c_int, C.POINTER(_i32p), _intp, _f32p,
@@ -144,6 +147,24 @@ def dds_run(func, xmin, xmax, xstart, nfunc_max, num_threads=0, sigma_init=0.2):
     fn = EVAL_FN(cb)
     best = lib().sac_dds_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, num_threads, sigma_init, fn, None,
                              _p(xbest, _f64p))
+    return best, xbest
+
+
+def de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.15):
+    """OptDE::run with a Python population evaluator func(X[P,D]) -> costs[P] (host only, no GPU needed)"""
+    xmin = np.ascontiguousarray(xmin, np.float64); xmax = np.ascontiguousarray(xmax, np.float64)
+    xstart = np.ascontiguousarray(xstart, np.float64)
+    D = len(xstart)
+    xbest = np.zeros(D)
+
+    def cb(Xp, P, Dd, costp, _user):
+        X = np.ctypeslib.as_array(Xp, shape=(P, Dd))
+        out = np.ctypeslib.as_array(costp, shape=(P,))
+        out[:] = np.asarray(func(X.copy()), np.float64)
+        return 0
+
+    fn = EVAL_FN(cb)
+    best = lib().sac_de_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, sigma_init, fn, None, _p(xbest, _f64p))
     return best, xbest
 
 

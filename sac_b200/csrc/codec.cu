@@ -81,6 +81,113 @@ void DdsSearch::consume(const double *costs)
 }
 
 // =====================================================================================================================
+// DE (src/opt/de.cpp). Random draws are made in the reference's order with freshly constructed libstdc++
+// distributions (common/rand.h), so that the trial vectors equal the reference's for the same costs.
+// =====================================================================================================================
+DeSearch::DeSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init)
+    : D_(D), nfunc_max_(nfunc_max), xmin_(xmin, xmin + D), xmax_(xmax, xmax + D), sigma_init_(sigma_init)
+{
+  xb_.first = 0.0;
+  xb_.second.assign(xstart, xstart + D);
+}
+double DeSearch::reflect(double xnew, double lo, double hi) const      // opt.cpp:156-166
+{
+  if (xnew < lo) { xnew = lo + (lo - xnew); if (xnew > hi) xnew = lo; }
+  if (xnew > hi) { xnew = hi - (xnew - hi); if (xnew < lo) xnew = hi; }
+  return xnew;
+}
+std::vector<int> DeSearch::select_k_unique_except(int n, int ie, int k)    // de.cpp:13-31
+{
+  std::vector<int> r;
+  if (k >= n - 1) return r;
+  std::vector<int> e(n);
+  for (int i = 0; i < n; i++) e[i] = i;
+  e.erase(std::remove(e.begin(), e.end(), ie), e.end());
+  for (int i = 0; i < k; i++) {
+    const int idx = (int)std::uniform_int_distribution<uint32_t>{0u, (uint32_t)(e.size() - 1)}(eng_);
+    const int val = e[idx];
+    r.push_back(val);
+    e.erase(std::remove(e.begin(), e.end(), val), e.end());
+  }
+  return r;
+}
+void DeSearch::propose(std::vector<std::vector<double>> &cands)
+{
+  cands.clear();
+  if (phase_ == 0) { cands.push_back(xb_.second); return; }
+  if (phase_ == 1) {                                                    // de.cpp:91-104: NP-1 normal samples around the start
+    pop_.assign(kNP, Point());
+    pop_[0] = xb_;
+    for (int a = 1; a < kNP; a++) {
+      std::vector<double> xt(D_);
+      for (int i = 0; i < D_; i++) {                                    // Opt::gen_norm (opt.cpp:111-116)
+        const double s = sigma_init_ * (xmax_[i] - xmin_[i]);
+        const double xnew = xb_.second[i] + s * std::normal_distribution<double>{0.0, 1.0}(eng_);
+        xt[i] = reflect(xnew, xmin_[i], xmax_[i]);
+      }
+      pop_[a].second = xt;
+      cands.push_back(xt);
+    }
+    return;
+  }
+  // ---- one generation (de.cpp:122-143) ----
+  std::sort(pop_.begin(), pop_.end(), [](const Point &a, const Point &b) { return a.first < b.first; });   // CURPBEST
+  const int num_agents = std::min(nfunc_max_ - nfunc_, (int)pop_.size());
+  gen_.assign(num_agents, Point());
+  gen_mut_.assign(num_agents, std::pair<double, double>());
+  for (int ia = 0; ia < num_agents; ia++) {                             // generate_candidate (de.cpp:33-71)
+    const double tCR = std::clamp(std::normal_distribution<double>{mCR_, 0.1}(eng_), 0.01, 1.0);
+    const double tF = std::clamp(std::cauchy_distribution<double>{mF_, 0.1}(eng_), 0.01, 1.0);
+    const int R = (int)std::uniform_int_distribution<uint32_t>{0u, (uint32_t)(D_ - 1)}(eng_);
+    const std::vector<int> v = select_k_unique_except((int)pop_.size(), ia, 2);
+    const int np = std::min(kNpBest, (int)pop_.size() - 1);
+    const int xp = np > 0 ? (int)std::uniform_int_distribution<uint32_t>{0u, (uint32_t)np}(eng_) : 0;
+    const std::vector<double> &xbest = pop_[xp].second, &xcur = pop_[ia].second, &x1 = pop_[v[0]].second, &x2 = pop_[v[1]].second;
+    std::vector<double> xm(D_), xtrial(D_);
+    for (int i = 0; i < D_; i++) {                                      // mut_curbest (de.cpp:175-183)
+      const double y = xcur[i] + tF * (xbest[i] - xcur[i]) + tF * (x1[i] - x2[i]);
+      xm[i] = reflect(y, xmin_[i], xmax_[i]);
+    }
+    for (int i = 0; i < D_; i++) {                                      // binomial cross-over: the event is drawn for every i
+      const bool ev = std::uniform_real_distribution<double>{0, 1}(eng_) < tCR;
+      xtrial[i] = (ev || i == R) ? xm[i] : xcur[i];
+    }
+    gen_mut_[ia] = {tCR, tF};
+    gen_[ia].second = xtrial;
+    cands.push_back(xtrial);
+  }
+}
+void DeSearch::consume(const double *costs)
+{
+  if (phase_ == 0) { xb_.first = costs[0]; nfunc_ = 1; phase_ = 1; return; }
+  if (phase_ == 1) {                                                    // de.cpp:106-111
+    for (int a = 1; a < kNP; a++) pop_[a].first = costs[a - 1];
+    nfunc_ += kNP - 1;
+    for (int a = 1; a < kNP; a++) if (pop_[a].first < xb_.first) xb_ = pop_[a];
+    phase_ = 2;
+    return;
+  }
+  const int num_agents = (int)gen_.size();
+  for (int ia = 0; ia < num_agents; ia++) gen_[ia].first = costs[ia];
+  nfunc_ += num_agents;
+  std::vector<double> CR_succ, F_succ;                                  // greedy selection (de.cpp:146-158)
+  for (int ia = 0; ia < num_agents; ia++)
+    if (gen_[ia].first < pop_[ia].first) {
+      pop_[ia] = gen_[ia];
+      CR_succ.push_back(gen_mut_[ia].first);
+      F_succ.push_back(gen_mut_[ia].second);
+      if (pop_[ia].first < xb_.first) xb_ = pop_[ia];
+    }
+  if (nfunc_ >= nfunc_max_) return;
+  double mean = 0.0;                                                    // MathUtils::mean / meanL (utils.h:283-304)
+  if (!CR_succ.empty()) { double s = 0.0; for (double x : CR_succ) s += x; mean = s / (double)CR_succ.size(); }
+  double meanl = 0.0;
+  if (!F_succ.empty()) { double s0 = 0.0, s1 = 0.0; for (double x : F_succ) { s0 += (x * x); s1 += x; } meanl = s1 > 0.0 ? s0 / s1 : 0.0; }
+  mCR_ = (1.0 - 0.1) * mCR_ + 0.1 * mean;
+  mF_ = (1.0 - 0.1) * mF_ + 0.1 * meanl;
+}
+
+// =====================================================================================================================
 // MD5
 // =====================================================================================================================
 namespace {
@@ -337,6 +444,10 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
                          const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                          const sac_window *const *resident = nullptr, const int32_t *resident_means = nullptr)
 {
+  if (cfg.search != SAC_SEARCH_DDS && cfg.search != SAC_SEARCH_DE) {
+    set_error("search method not supported (--opt-cfg=cma is a strictly sequential (1+1)-ES: not built)");
+    return SAC_E_UNSUPPORTED;
+  }
   if (cfg.frame_parallel == 2 && nframes > 1)
     return frames_encode_streams(e, cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, out, resident, resident_means);
   return frames_encode_seq(e, cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, out, resident, resident_means);
@@ -456,13 +567,14 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
     const int groups = cfg.frame_parallel == 1 ? 1 : nframes;     // frames searched together per group
     for (int g = 0; g < groups; g++) {
       const int f0 = cfg.frame_parallel == 1 ? 0 : g, f1 = cfg.frame_parallel == 1 ? nframes : g + 1;
-      std::vector<std::unique_ptr<DdsSearch>> ss;
+      std::vector<std::unique_ptr<Search>> ss;
       std::vector<int> wfrom, wn;
       for (int f = f0; f < f1; f++) {
         if (cfg.reset) base_reset(fw[f].profile); else std::memcpy(fw[f].profile, cur, sizeof(cur));
         std::vector<double> xs(D);
         for (int i = 0; i < D; i++) xs[i] = fw[f].profile[dims[i]];
-        ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma));
+        if (cfg.search == SAC_SEARCH_DE) ss.emplace_back(new DeSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.sigma));
+        else ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma));
         const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
         wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
       }
@@ -776,6 +888,26 @@ double sac_dds_run(int D, const double *xmin, const double *xmax, const double *
   return s.best_cost();
 }
 
+double sac_de_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init, sac_eval_fn eval,
+                  void *user, double *xbest)
+{
+  if (D <= 0 || !xmin || !xmax || !xstart || !eval || nfunc_max < 1) { set_error("sac_de_run: bad argument"); return std::numeric_limits<double>::quiet_NaN(); }
+  DeSearch s(D, xmin, xmax, xstart, nfunc_max, sigma_init);
+  std::vector<std::vector<double>> cands;
+  std::vector<double> X, cost;
+  do {
+    s.propose(cands);
+    if (cands.empty()) break;
+    X.clear();
+    for (auto &c : cands) X.insert(X.end(), c.begin(), c.end());
+    cost.assign(cands.size(), 0.0);
+    if (eval(X.data(), (int)cands.size(), D, cost.data(), user)) { set_error("sac_de_run: evaluator aborted"); break; }
+    s.consume(cost.data());
+  } while (!s.done());
+  if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);
+  return s.best_cost();
+}
+
 int sac_bitplane_encode(sac_engine *h, const int32_t *resid, int n, int *maxbpn_io, uint8_t *out, long long cap, long long *out_len)
 {
   Engine *e = reinterpret_cast<Engine *>(h);
@@ -844,7 +976,7 @@ void sac_cfg_default(sac_cfg *c)
   std::memset(c, 0, sizeof(*c));
   c->optimize = 0; c->fraction = 0; c->maxnfunc = 0; c->num_threads = 0; c->sigma = 0.2; c->optk = 4;
   c->cost_kind = SAC_COST_ENTROPY; c->reset = 0; c->zero_mean = 1; c->sparse_pcm = 1; c->max_framelen = 20; c->adapt_block = 1;
-  c->frame_parallel = 0; c->verbose = 0;
+  c->frame_parallel = 0; c->verbose = 0; c->search = SAC_SEARCH_DDS;
 }
 int sac_cfg_preset(sac_cfg *c, const char *name)                        // cmdline.cpp:127-156
 {

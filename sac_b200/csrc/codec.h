@@ -4,23 +4,37 @@
 #include <cstdint>
 #include <random>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace sacb {
 
-// ---- DDS as a resumable state machine (OptDDS::run_single / run_mt, /root/reference src/opt/dds.cpp:33-106) so that
-// several searches (frames) can share one GPU batch per generation.
-class DdsSearch {
+// ---- searches as resumable state machines so that several of them (frames) can share one GPU batch per generation:
+// propose() hands out the candidates of the next generation (first call: the start vector alone), consume() takes
+// their costs in the same order.
+class Search {
+public:
+  virtual ~Search() {}
+  virtual bool done() const = 0;
+  virtual void propose(std::vector<std::vector<double>> &cands) = 0;
+  virtual void consume(const double *costs) = 0;
+  virtual const std::vector<double> &best_x() const = 0;
+  virtual double best_cost() const = 0;
+  virtual double sigma() const = 0;
+  virtual int nfunc() const = 0;
+};
+
+// DDS (OptDDS::run_single / run_mt, /root/reference src/opt/dds.cpp:33-106)
+class DdsSearch : public Search {
 public:
   DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads, double sigma_init);
-  bool done() const { return started_ && nfunc_ >= nfunc_max_; }
-  // candidates of the next generation (first call: the start vector alone)
-  void propose(std::vector<std::vector<double>> &cands);
-  void consume(const double *costs);
-  const std::vector<double> &best_x() const { return xb_; }
-  double best_cost() const { return fb_; }
-  double sigma() const { return sigma_; }
-  int nfunc() const { return nfunc_; }
+  bool done() const override { return started_ && nfunc_ >= nfunc_max_; }
+  void propose(std::vector<std::vector<double>> &cands) override;
+  void consume(const double *costs) override;
+  const std::vector<double> &best_x() const override { return xb_; }
+  double best_cost() const override { return fb_; }
+  double sigma() const override { return sigma_; }
+  int nfunc() const override { return nfunc_; }
 
 private:
   std::vector<double> candidate(int nfunc);
@@ -34,6 +48,38 @@ private:
   int nsucc_ = 0, nfail_ = 0;                 // SSC0(3,50)
   double p_succ_ = 0.05;                      // SSC1(0.05,0.10,0.05)
   std::vector<std::vector<double>> pending_;
+};
+
+// Differential evolution, the reference's --opt-cfg=de (OptDE, src/opt/de.cpp, de.h: JADE-style current-to-pbest/1/bin,
+// NP = 30, adaptive CR / F). A generation is NP trial vectors: it maps onto one population evaluation as is.
+class DeSearch : public Search {
+public:
+  DeSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init);
+  bool done() const override { return phase_ == 2 && nfunc_ >= nfunc_max_; }
+  void propose(std::vector<std::vector<double>> &cands) override;
+  void consume(const double *costs) override;
+  const std::vector<double> &best_x() const override { return xb_.second; }
+  double best_cost() const override { return xb_.first; }
+  double sigma() const override { return mF_; }
+  int nfunc() const override { return nfunc_; }
+
+private:
+  typedef std::pair<double, std::vector<double>> Point;    // Opt::ppoint (opt.h:14)
+  double reflect(double xnew, double lo, double hi) const;
+  std::vector<int> select_k_unique_except(int n, int ie, int k);
+  std::mt19937 eng_{0};                       // Opt::rand, seed 0 (opt.cpp:5)
+  int D_, nfunc_max_;
+  std::vector<double> xmin_, xmax_;
+  double sigma_init_;
+  // DECfg defaults (de.h:18-31)
+  static constexpr int kNP = 30;
+  static constexpr int kNpBest = 2;           // clamp(round(0.1 * 30) - 1, 0, 29)
+  double mCR_ = 0.5, mF_ = 0.5;
+  std::vector<Point> pop_, gen_;
+  std::vector<std::pair<double, double>> gen_mut_;
+  Point xb_;
+  int nfunc_ = 0;
+  int phase_ = 0;                             // 0: start vector, 1: initial population, 2: generations
 };
 
 // ---- MD5 (RFC 1321) over the raw PCM bytes, as the reference stores in the .sac header ----

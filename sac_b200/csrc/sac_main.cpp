@@ -152,7 +152,12 @@ int main(int argc, const char *argv[])
       else if (key == "--OPT-RESET") cfg.reset = 1;
       else if (key == "--OPT-CFG") {
         auto vs = split(val, ',');
-        if (vs.size() >= 1 && vs[0] != "DDS") std::cerr << "  warning: only opt='DDS' is implemented\n";
+        if (vs.size() >= 1) {                                            // cmdline.cpp:198-204
+          if (vs[0] == "DDS") cfg.search = SAC_SEARCH_DDS;
+          else if (vs[0] == "DE") cfg.search = SAC_SEARCH_DE;
+          else if (vs[0] == "CMA") cfg.search = SAC_SEARCH_CMA;           // rejected by the library: not built
+          else std::cerr << "  warning: invalid opt='" << vs[0] << "'\n";
+        }
         if (vs.size() >= 2) cfg.num_threads = std::clamp(std::atoi(vs[1].c_str()), 0, 4096);
         if (vs.size() >= 3) cfg.sigma = std::clamp(std::atof(vs[2].c_str()), 0., 1.);
       } else if (key == "--ADAPT-BLOCK") cfg.adapt_block = !(val == "NO" || val == "0");
@@ -179,7 +184,8 @@ int main(int argc, const char *argv[])
     std::printf("  Profile: %ds%s%s\n", cfg.max_framelen, cfg.zero_mean ? " zero-mean" : "", cfg.frame_parallel ? " frame-parallel" : "");
     if (cfg.optimize) {
       const char *cs[] = {"L1", "rms", "ent", "glb", "bpn"};
-      std::printf("  Optimize: DDS %.1f%%,n=%d,%s,k=%d,gen=%d\n", cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk, cfg.num_threads);
+      std::printf("  Optimize: %s %.1f%%,n=%d,%s,k=%d,gen=%d\n", cfg.search == SAC_SEARCH_DE ? "DE" : (cfg.search == SAC_SEARCH_CMA ? "CMA" : "DDS"),
+                  cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk, cfg.search == SAC_SEARCH_DE ? 30 : cfg.num_threads);
     }
     rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
     if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }

@@ -63,6 +63,9 @@ def ref_lib(nc=True):
     lib.ref_cost.restype = C.c_double
     lib.ref_dds_run.restype = C.c_double
     lib.ref_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, COST_CB, C.c_void_p, _f64p]
+    if hasattr(lib, "ref_de_run"):
+        lib.ref_de_run.restype = C.c_double
+        lib.ref_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, COST_CB, C.c_void_p, _f64p]
     for f in ("ref_frame_free", "ref_frame_set_samples", "ref_frame_analyse", "ref_frame_get_stats", "ref_frame_set_stats",
               "ref_frame_set_profile", "ref_frame_get_profile", "ref_frame_predict_window", "ref_frame_predict",
               "ref_frame_encode", "ref_frame_get_error", "ref_frame_get_encoded", "ref_frame_set_mt"):

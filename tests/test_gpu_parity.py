@@ -269,3 +269,20 @@ def test_dedup_of_identical_chains_is_exact(engine):
     engine.set_dedup(prev)
     assert np.array_equal(r_on, r_off)
     win.close()
+
+
+def test_frame_encode_with_de_search_roundtrips(engine):
+    """--opt-cfg=de through the frame seam: DE generations (start vector, 29 initial samples, trial vectors) evaluated as
+    populations, the record decodes bit-exactly and is not larger than the unoptimised one; cma is rejected loudly"""
+    pcm = synth_pcm(0.5, 2, 31).astype(np.int32)
+    raw = [pcm[:, 0], pcm[:, 1]]
+    base, _ = engine.frames_encode(sb.make_cfg("normal", max_framelen=1), [raw], 44100)
+    cfg = sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=36, sigma=0.2, cost_kind=sb.COST_BITPLANE, max_framelen=1, search=sb.SEARCH_DE)
+    l0 = engine.launches
+    rec, prof = engine.frames_encode(cfg, [raw], 44100)
+    assert engine.launches - l0 == 3 * 3 + 3           # 3 population evaluations + the final pass, 3 kernels each
+    dec, used = engine.frame_decode(2, rec, 44100)
+    assert used == len(rec) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1])
+    assert len(rec) <= len(base)
+    with pytest.raises(sb.SacError):
+        engine.frames_encode(sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=8, max_framelen=1, search=sb.SEARCH_CMA), [raw], 44100)

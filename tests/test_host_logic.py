@@ -104,3 +104,31 @@ def test_cli_listing_of_a_reference_file_matches_the_reference_cli():
         got = out[out.index("Open:"):].splitlines()
         want = open(os.path.join(gold, "ref_stereo_quarter_normal.%s.txt" % ext)).read().splitlines()
         assert got == want, (flag, got, want)
+
+
+def test_de_driver_matches_reference_goldens():
+    """sac_de_run (product, --opt-cfg=de) against traces recorded from the reference's OptDE (tests/golden/make_golden_de.py):
+    every evaluated vector in order, the incumbent and its cost -- including a cost function with ties (std::sort order)
+    and nfunc_max below the population size"""
+    import hashlib, json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_de.json")))
+    vmin, vmax, vdef = sb.base_profile()
+    idx = list(sb.SEARCH_DIMS)
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    sha = lambda a: hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for c in g["cases"]:
+        trace = []
+
+        def f(X):
+            out = []
+            for x in X:
+                trace.append(x.copy())
+                z = (x - xmin) / (xmax - xmin)
+                v = float(np.sum((z - 0.37) ** 2) + 0.05 * np.sum(np.cos(9 * z)))
+                out.append(float(np.floor(v * 8)) if c["ties"] else v)
+            return out
+
+        best, xb = sb.de_run(f, xmin, xmax, xs, c["nfunc"], c["sigma"])
+        assert len(trace) == c["evals"], c
+        assert sha(np.stack(trace)) == c["trace_sha1"], c
+        assert best == c["best"] and sha(xb) == c["xbest_sha1"], c
