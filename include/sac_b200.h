@@ -106,6 +106,9 @@ double sac_dds_run(int D, const double *xmin, const double *xmax, const double *
  * the start vector, then the 29 initial samples, then generations of up to 30 trial vectors */
 double sac_de_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
                   sac_eval_fn eval, void *user, double *xbest);
+/* OptCMA::run (src/opt/cma.cpp:55-92): (1+1)-CMA-ES, one evaluation per step (P is always 1) */
+double sac_cma_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
+                   sac_eval_fn eval, void *user, double *xbest);
 
 /* ---- frame coding ------------------------------------------------------------------------------------------------ */
 enum { SAC_SEARCH_DDS = 0, SAC_SEARCH_DE = 1, SAC_SEARCH_CMA = 2 };   /* FrameCoder::SearchMethod (src/libsac/libsac.h) */
@@ -125,7 +128,7 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
   int frame_parallel;           /* B200 extension (implies --opt-reset semantics): 1 = all frames of a call share each generation's launches,
                                    2 = every frame runs on its own stream / host thread, all concurrently on the GPU */
   int verbose;
-  int search;                   /* SAC_SEARCH_*: --opt-cfg=dds|de (src/cmdline.cpp:195-206); cma is not built */
+  int search;                   /* SAC_SEARCH_*: --opt-cfg=dds|de|cma (src/cmdline.cpp:195-206) */
 } sac_cfg;
 void sac_cfg_default(sac_cfg *);
 /* presets of src/cmdline.cpp:127-156: "normal","high","veryhigh","extrahigh","best","insane" */

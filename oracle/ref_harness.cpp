@@ -39,6 +39,7 @@
 #include "libsac/vle.h"
 #include "opt/dds.h"
 #include "opt/de.h"
+#include "opt/cma.h"
 #include "opt/ssc.h"
 #undef private
 #undef protected
@@ -276,6 +277,20 @@ double ref_de_run(int ndim, const double *xmin, const double *xmax, const double
   OptDE de(cfg, pb, false);
   vec1D xs(xstart, xstart + ndim);
   Opt::ppoint r = de.run([&](const vec1D &x) { return cb(x.data(), ndim, user); }, xs);
+  std::copy_n(r.second.begin(), ndim, xbest);
+  return r.first;
+}
+// ---- CMA (src/opt/cma.cpp) -----------------------------------------------------------------------------------------
+double ref_cma_run(int ndim, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
+                   ref_cost_cb cb, void *user, double *xbest)
+{
+  Opt::box_const pb(ndim);
+  for (int i = 0; i < ndim; i++) { pb[i].xmin = xmin[i]; pb[i].xmax = xmax[i]; }
+  OptCMA::CMACfg cfg;
+  cfg.nfunc_max = nfunc_max; cfg.num_threads = 1; cfg.sigma_init = sigma_init;
+  OptCMA cma(cfg, pb, false);
+  vec1D xs(xstart, xstart + ndim);
+  Opt::ppoint r = cma.run([&](const vec1D &x) { return cb(x.data(), ndim, user); }, xs);
   std::copy_n(r.second.begin(), ndim, xbest);
   return r.first;
 }

@@ -86,6 +86,8 @@ def lib():
         L.sac_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
         L.sac_de_run.restype = C.c_double
         L.sac_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
+        L.sac_cma_run.restype = C.c_double
+        L.sac_cma_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
         L.sac_cfg_default.argtypes = [C.POINTER(Cfg)]
         L.sac_cfg_preset.argtypes = [C.POINTER(Cfg), C.c_char_p]
         L.sac_frames_encode.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_int, C.c_int, C.c_int, C.POINTER(_i32p), _intp, _f32p,
@@ -150,8 +152,9 @@ def dds_run(func, xmin, xmax, xstart, nfunc_max, num_threads=0, sigma_init=0.2):
     return best, xbest
 
 
-def de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.15):
-    """OptDE::run with a Python population evaluator func(X[P,D]) -> costs[P] (host only, no GPU needed)"""
+def de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.15, entry="sac_de_run"):
+    """OptDE::run (or, entry="sac_cma_run", OptCMA::run) with a Python population evaluator func(X[P,D]) -> costs[P]
+    (host only, no GPU needed)"""
     xmin = np.ascontiguousarray(xmin, np.float64); xmax = np.ascontiguousarray(xmax, np.float64)
     xstart = np.ascontiguousarray(xstart, np.float64)
     D = len(xstart)
@@ -164,8 +167,12 @@ def de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.15):
         return 0
 
     fn = EVAL_FN(cb)
-    best = lib().sac_de_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, sigma_init, fn, None, _p(xbest, _f64p))
+    best = getattr(lib(), entry)(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, sigma_init, fn, None, _p(xbest, _f64p))
     return best, xbest
+
+
+def cma_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.0):
+    return de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init, entry="sac_cma_run")
 
 
 class Window:

@@ -188,6 +188,104 @@ void DeSearch::consume(const double *costs)
 }
 
 // =====================================================================================================================
+// CMA (src/opt/cma.cpp): (1+1)-ES with covariance adaptation; same draws and operation order as the reference
+// =====================================================================================================================
+namespace {
+// slmath::dot (common/math.h:130-161): two 4-lane fma accumulators over blocks of 8, lane sums, then libstdc++'s
+// transform_reduce shape for the tail (blocks of 4 as (a0+a1)+(a2+a3), then one by one)
+double slmath_dot(const double *x, const double *y, size_t n)
+{
+  double total = 0.0;
+  size_t i = 0;
+  if (n >= 8) {
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (; i + 8 <= n; i += 8)
+      for (int l = 0; l < 4; l++) { s1[l] = std::fma(x[i + l], y[i + l], s1[l]); s2[l] = std::fma(x[i + 4 + l], y[i + 4 + l], s2[l]); }
+    for (int l = 0; l < 4; l++) s1[l] = s1[l] + s2[l];
+    total = s1[0] + s1[1] + s1[2] + s1[3];
+  }
+  double init = 0.0;
+  while (n - i >= 4) {
+    const double v1 = x[i] * y[i] + x[i + 1] * y[i + 1];
+    const double v2 = x[i + 2] * y[i + 2] + x[i + 3] * y[i + 3];
+    init = init + (v1 + v2);
+    i += 4;
+  }
+  for (; i < n; i++) init = init + x[i] * y[i];
+  total += init;
+  return total;
+}
+} // namespace
+
+CmaSearch::CmaSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init)
+    : D_(D), nfunc_max_(nfunc_max), xmin_(xmin, xmin + D), xmax_(xmax, xmax + D), xb_(xstart, xstart + D), pc_(D, 0.0), az_(D, 0.0),
+      mcov_(D, std::vector<double>(D, 0.0)), G_(D, std::vector<double>(D, 0.0)), sigma_(sigma_init)
+{
+  const double n = (double)D;
+  dinv_ = 1.0 / (1.0 + n / 2.0);                                        // SSC1 p_d = 1/d
+  p_target_ = 2.0 / 11.0;
+  cp_ = 1.0 / 12.0;
+  cc_ = 2.0 / (n + 2.0);
+  ccov_ = 2.0 / (n * n + 6.0);
+  p_succ_ = p_target_;
+  for (int i = 0; i < D; i++) mcov_[i][i] = 1.0;
+}
+double CmaSearch::reflect(double xnew, double lo, double hi) const
+{
+  if (xnew < lo) { xnew = lo + (lo - xnew); if (xnew > hi) xnew = lo; }
+  if (xnew > hi) { xnew = hi - (xnew - hi); if (xnew < lo) xnew = hi; }
+  return xnew;
+}
+void CmaSearch::propose(std::vector<std::vector<double>> &cands)
+{
+  cands.clear();
+  if (!started_) { cands.push_back(xb_); return; }
+  // chol.Factor(mcov, 0.1) (math.h:89-111); a failed factorisation leaves G partially updated, as in the reference
+  {
+    const double ftol = 1E-8;
+    for (int i = 0; i < D_; i++) std::copy_n(mcov_[i].begin(), i + 1, G_[i].begin());
+    for (int i = 0; i < D_; i++) {
+      for (int j = 0; j < i; j++) {
+        double sum = G_[i][j];
+        for (int k = 0; k < j; k++) sum -= (G_[i][k] * G_[j][k]);
+        G_[i][j] = sum / G_[j][j];
+      }
+      double sum = G_[i][i] + 0.1;
+      for (int k = 0; k < i; k++) sum -= (G_[i][k] * G_[i][k]);
+      if (sum > ftol) G_[i][i] = std::sqrt(sum); else break;
+    }
+  }
+  std::vector<double> z(D_);
+  for (auto &r : z) r = std::normal_distribution<double>{0.0, 1.0}(eng_);
+  for (int i = 0; i < D_; i++) az_[i] = slmath_dot(G_[i].data(), z.data(), (size_t)D_);   // slmath::mul(chol.G, z): full rows of G
+  xgen_.assign(D_, 0.0);
+  for (int i = 0; i < D_; i++) {
+    const double scale = (xmax_[i] - xmin_[i]) * sigma_;
+    const double xnew = xb_[i] + scale * az_[i];
+    xgen_[i] = reflect(xnew, xmin_[i], xmax_[i]);
+  }
+  cands.push_back(xgen_);
+}
+void CmaSearch::consume(const double *costs)
+{
+  if (!started_) { fb_ = costs[0]; nfunc_ = 1; started_ = true; return; }
+  const double fn = costs[0];
+  const double lambda = (fn < fb_) ? 1.0 : 0.0;
+  p_succ_ = (1.0 - cp_) * p_succ_ + cp_ * lambda;                       // SSC1::update (ssc.h:49-55)
+  sigma_ = sigma_ * std::exp(dinv_ * (p_succ_ - p_target_) / (1.0 - p_target_));
+  sigma_ = std::clamp(sigma_, 0.05, 0.25);
+  if (fn < fb_) {
+    fb_ = fn;
+    xb_ = xgen_;
+    const double a = 1.0 - cc_, b = std::sqrt(cc_ * (2.0 - cc_));       // update_cov (cma.cpp:49-53)
+    for (int i = 0; i < D_; i++) pc_[i] = a * pc_[i] + b * az_[i];
+    for (int j = 0; j < D_; j++)
+      for (int i = 0; i < D_; i++) mcov_[j][i] = (1.0 - ccov_) * mcov_[j][i] + ccov_ * (pc_[j] * pc_[i]);
+  }
+  nfunc_++;
+}
+
+// =====================================================================================================================
 // MD5
 // =====================================================================================================================
 namespace {
@@ -444,9 +542,9 @@ static int frames_encode(Engine *e, const sac_cfg &cfg, int nch, int max_framesi
                          const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                          const sac_window *const *resident = nullptr, const int32_t *resident_means = nullptr)
 {
-  if (cfg.search != SAC_SEARCH_DDS && cfg.search != SAC_SEARCH_DE) {
-    set_error("search method not supported (--opt-cfg=cma is a strictly sequential (1+1)-ES: not built)");
-    return SAC_E_UNSUPPORTED;
+  if (cfg.search != SAC_SEARCH_DDS && cfg.search != SAC_SEARCH_DE && cfg.search != SAC_SEARCH_CMA) {
+    set_error("unknown search method");
+    return SAC_E_ARG;
   }
   if (cfg.frame_parallel == 2 && nframes > 1)
     return frames_encode_streams(e, cfg, nch, max_framesize, nframes, planes, numsamples, profile_io, out, resident, resident_means);
@@ -574,6 +672,7 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
         std::vector<double> xs(D);
         for (int i = 0; i < D; i++) xs[i] = fw[f].profile[dims[i]];
         if (cfg.search == SAC_SEARCH_DE) ss.emplace_back(new DeSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.sigma));
+        else if (cfg.search == SAC_SEARCH_CMA) ss.emplace_back(new CmaSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, 0.0));   // cma_cfg.sigma_init stays 0 (cmdline.cpp:232-235)
         else ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma));
         const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
         wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
@@ -902,6 +1001,22 @@ double sac_de_run(int D, const double *xmin, const double *xmax, const double *x
     for (auto &c : cands) X.insert(X.end(), c.begin(), c.end());
     cost.assign(cands.size(), 0.0);
     if (eval(X.data(), (int)cands.size(), D, cost.data(), user)) { set_error("sac_de_run: evaluator aborted"); break; }
+    s.consume(cost.data());
+  } while (!s.done());
+  if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);
+  return s.best_cost();
+}
+
+double sac_cma_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init, sac_eval_fn eval,
+                   void *user, double *xbest)
+{
+  if (D <= 0 || !xmin || !xmax || !xstart || !eval || nfunc_max < 1) { set_error("sac_cma_run: bad argument"); return std::numeric_limits<double>::quiet_NaN(); }
+  CmaSearch s(D, xmin, xmax, xstart, nfunc_max, sigma_init);
+  std::vector<std::vector<double>> cands;
+  std::vector<double> cost(1);
+  do {
+    s.propose(cands);
+    if (eval(cands[0].data(), 1, D, cost.data(), user)) { set_error("sac_cma_run: evaluator aborted"); break; }
     s.consume(cost.data());
   } while (!s.done());
   if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);

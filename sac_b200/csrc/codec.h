@@ -82,6 +82,31 @@ private:
   int phase_ = 0;                             // 0: start vector, 1: initial population, 2: generations
 };
 
+// (1+1)-CMA-ES, the reference's --opt-cfg=cma (OptCMA, src/opt/cma.cpp, cma.h; Cholesky of the covariance with 0.1
+// regularisation per step, SSC1 step-size control). Strictly one evaluation per step.
+class CmaSearch : public Search {
+public:
+  CmaSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init);
+  bool done() const override { return started_ && nfunc_ >= nfunc_max_; }
+  void propose(std::vector<std::vector<double>> &cands) override;
+  void consume(const double *costs) override;
+  const std::vector<double> &best_x() const override { return xb_; }
+  double best_cost() const override { return fb_; }
+  double sigma() const override { return sigma_; }
+  int nfunc() const override { return nfunc_; }
+
+private:
+  double reflect(double xnew, double lo, double hi) const;
+  std::mt19937 eng_{0};
+  int D_, nfunc_max_;
+  std::vector<double> xmin_, xmax_, xb_, pc_, az_, xgen_;
+  std::vector<std::vector<double>> mcov_, G_;
+  double fb_ = 0.0, sigma_;
+  double cc_, ccov_, p_target_, cp_, dinv_, p_succ_;     // CMAParams (cma.h:21-37), SSC1 state
+  int nfunc_ = 0;
+  bool started_ = false;
+};
+
 // ---- MD5 (RFC 1321) over the raw PCM bytes, as the reference stores in the .sac header ----
 struct Md5 {
   uint32_t a, b, c, d;

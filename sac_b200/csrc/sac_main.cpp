@@ -155,7 +155,7 @@ int main(int argc, const char *argv[])
         if (vs.size() >= 1) {                                            // cmdline.cpp:198-204
           if (vs[0] == "DDS") cfg.search = SAC_SEARCH_DDS;
           else if (vs[0] == "DE") cfg.search = SAC_SEARCH_DE;
-          else if (vs[0] == "CMA") cfg.search = SAC_SEARCH_CMA;           // rejected by the library: not built
+          else if (vs[0] == "CMA") cfg.search = SAC_SEARCH_CMA;
           else std::cerr << "  warning: invalid opt='" << vs[0] << "'\n";
         }
         if (vs.size() >= 2) cfg.num_threads = std::clamp(std::atoi(vs[1].c_str()), 0, 4096);

@@ -1,5 +1,6 @@
-"""Goldens for the DE search (src/opt/de.cpp) recorded from the reference's own OptDE through oracle/_ref/libsacref_nc.so
-(ref_harness.cpp: ref_de_run, one evaluation thread, so the trace is in the reference's generation order).
+"""Goldens for the DE and CMA searches (src/opt/de.cpp, src/opt/cma.cpp) recorded from the reference's own OptDE / OptCMA through
+oracle/_ref/libsacref_nc.so (ref_harness.cpp: ref_de_run / ref_cma_run, one evaluation thread, so the traces are in the
+reference's evaluation order).
 usage: python tests/golden/make_golden_de.py   (needs /root/reference via oracle/_ref; writes tests/golden/golden_de.json)"""
 import hashlib, json, os, sys
 import numpy as np
@@ -37,6 +38,20 @@ def main():
         fb = ref.ref_de_run(56, ol._p(xmin, ol._f64p), ol._p(xmax, ol._f64p), ol._p(xs, ol._f64p), nfunc, sigma, fn, None, ol._p(xb, ol._f64p))
         out["cases"].append(dict(nfunc=nfunc, sigma=sigma, ties=ties, best=float(fb), xbest_sha1=sha(xb), trace_sha1=sha(np.stack(trace)),
                                  evals=len(trace)))
+    out["cma"] = []
+    for nfunc, sigma, ties in ((80, 0.0, False), (400, 0.1, False), (250, 0.0, True)):
+        trace = []
+
+        def cb2(xp, n, _u):
+            x = np.ctypeslib.as_array(xp, shape=(n,)).copy()
+            trace.append(x)
+            return cost_of(x, xmin, xmax, ties)
+
+        fn = ol.COST_CB(cb2)
+        xb = np.zeros(56)
+        fb = ref.ref_cma_run(56, ol._p(xmin, ol._f64p), ol._p(xmax, ol._f64p), ol._p(xs, ol._f64p), nfunc, sigma, fn, None, ol._p(xb, ol._f64p))
+        out["cma"].append(dict(nfunc=nfunc, sigma=sigma, ties=ties, best=float(fb), xbest_sha1=sha(xb), trace_sha1=sha(np.stack(trace)),
+                               evals=len(trace)))
     json.dump(out, open(os.path.join(HERE, "golden_de.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 

@@ -63,6 +63,9 @@ def ref_lib(nc=True):
     lib.ref_cost.restype = C.c_double
     lib.ref_dds_run.restype = C.c_double
     lib.ref_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, COST_CB, C.c_void_p, _f64p]
+    if hasattr(lib, "ref_cma_run"):
+        lib.ref_cma_run.restype = C.c_double
+        lib.ref_cma_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, COST_CB, C.c_void_p, _f64p]
     if hasattr(lib, "ref_de_run"):
         lib.ref_de_run.restype = C.c_double
         lib.ref_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, COST_CB, C.c_void_p, _f64p]

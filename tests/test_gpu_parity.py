@@ -272,8 +272,8 @@ def test_dedup_of_identical_chains_is_exact(engine):
 
 
 def test_frame_encode_with_de_search_roundtrips(engine):
-    """--opt-cfg=de through the frame seam: DE generations (start vector, 29 initial samples, trial vectors) evaluated as
-    populations, the record decodes bit-exactly and is not larger than the unoptimised one; cma is rejected loudly"""
+    """--opt-cfg=de / cma through the frame seam: DE generations (start vector, 29 initial samples, trial vectors) evaluated
+    as populations, CMA one candidate per step; the records decode bit-exactly and are not larger than the unoptimised one"""
     pcm = synth_pcm(0.5, 2, 31).astype(np.int32)
     raw = [pcm[:, 0], pcm[:, 1]]
     base, _ = engine.frames_encode(sb.make_cfg("normal", max_framelen=1), [raw], 44100)
@@ -284,5 +284,9 @@ def test_frame_encode_with_de_search_roundtrips(engine):
     dec, used = engine.frame_decode(2, rec, 44100)
     assert used == len(rec) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1])
     assert len(rec) <= len(base)
+    rec2, _ = engine.frames_encode(sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=6, cost_kind=sb.COST_ENTROPY, max_framelen=1,
+                                               search=sb.SEARCH_CMA), [raw], 44100)
+    dec, used = engine.frame_decode(2, rec2, 44100)
+    assert used == len(rec2) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1])
     with pytest.raises(sb.SacError):
-        engine.frames_encode(sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=8, max_framelen=1, search=sb.SEARCH_CMA), [raw], 44100)
+        engine.frames_encode(sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=8, max_framelen=1, search=7), [raw], 44100)

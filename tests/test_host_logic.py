@@ -106,7 +106,7 @@ def test_cli_listing_of_a_reference_file_matches_the_reference_cli():
         assert got == want, (flag, got, want)
 
 
-def test_de_driver_matches_reference_goldens():
+def test_de_and_cma_drivers_match_reference_goldens():
     """sac_de_run (product, --opt-cfg=de) against traces recorded from the reference's OptDE (tests/golden/make_golden_de.py):
     every evaluated vector in order, the incumbent and its cost -- including a cost function with ties (std::sort order)
     and nfunc_max below the population size"""
@@ -129,6 +129,13 @@ def test_de_driver_matches_reference_goldens():
             return out
 
         best, xb = sb.de_run(f, xmin, xmax, xs, c["nfunc"], c["sigma"])
+        assert len(trace) == c["evals"], c
+        assert sha(np.stack(trace)) == c["trace_sha1"], c
+        assert best == c["best"] and sha(xb) == c["xbest_sha1"], c
+    # OptCMA (--opt-cfg=cma): (1+1)-ES, Cholesky of the adapted covariance every step, sigma bootstrapping from 0
+    for c in g["cma"]:
+        trace = []
+        best, xb = sb.cma_run(f, xmin, xmax, xs, c["nfunc"], c["sigma"])
         assert len(trace) == c["evals"], c
         assert sha(np.stack(trace)) == c["trace_sha1"], c
         assert best == c["best"] and sha(xb) == c["xbest_sha1"], c
