@@ -112,6 +112,12 @@ double sac_cma_run(int D, const double *xmin, const double *xmax, const double *
 
 /* ---- frame coding ------------------------------------------------------------------------------------------------ */
 enum { SAC_SEARCH_DDS = 0, SAC_SEARCH_DE = 1, SAC_SEARCH_CMA = 2 };   /* FrameCoder::SearchMethod (src/libsac/libsac.h) */
+/* Codec::Analyse for one read of `numsamples` raw samples (host only, no GPU): 3-s blocks are classed by the sparse-PCM
+ * cost ratio (> 1.35), runs of equal class become sub-frames (start/length/state, at most `cap` written). Returns
+ * the number of sub-frames. */
+int sac_analyse_subframes(int nch, const int32_t *const *planes, int numsamples, int samplerate, int *start, int *length,
+                          int *state, int cap);
+
 typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac/libsac.h:19-44) */
   int optimize;                 /* 0 = --normal */
   double fraction;              /* window fraction of max_framesize */
@@ -122,9 +128,9 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
   int cost_kind;                /* SAC_COST_* */
   int reset;                    /* --opt-reset: every frame starts from the base profile */
   int zero_mean;                /* 1 */
-  int sparse_pcm;               /* accepted for CLI compatibility; sparse mapping is not implemented (never smaller below ratio 1.05) */
+  int sparse_pcm;               /* accepted for CLI compatibility; rank-mapped coding of sparse frames is not implemented (frames are coded unmapped) */
   int max_framelen;             /* seconds (20) */
-  int adapt_block;              /* accepted; adaptive splitting is not implemented (one sub-frame per read) */
+  int adapt_block;              /* adaptive sub-frame split of every max_framelen read (Codec::Analyse, libsac.cpp:726-780) */
   int frame_parallel;           /* B200 extension (implies --opt-reset semantics): 1 = all frames of a call share each generation's launches,
                                    2 = every frame runs on its own stream / host thread, all concurrently on the GPU */
   int verbose;

@@ -84,6 +84,7 @@ def lib():
                                     C.c_int, C.c_int, _f64p]
         L.sac_dds_run.restype = C.c_double
         L.sac_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
+        L.sac_analyse_subframes.argtypes = [C.c_int, C.POINTER(_i32p), C.c_int, C.c_int, _intp, _intp, _intp, C.c_int]
         L.sac_de_run.restype = C.c_double
         L.sac_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
         L.sac_cma_run.restype = C.c_double
@@ -150,6 +151,18 @@ def dds_run(func, xmin, xmax, xstart, nfunc_max, num_threads=0, sigma_init=0.2):
     best = lib().sac_dds_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, num_threads, sigma_init, fn, None,
                              _p(xbest, _f64p))
     return best, xbest
+
+
+def analyse_subframes(planes, samplerate):
+    """Codec::Analyse for one read (host only): [(start, length, state)]"""
+    planes = [np.ascontiguousarray(p, np.int32) for p in planes]
+    arr = (_i32p * len(planes))(*[_p(p, _i32p) for p in planes])
+    cap = 64
+    st = np.zeros(cap, np.int32); ln = np.zeros(cap, np.int32); ss = np.zeros(cap, np.int32)
+    n = lib().sac_analyse_subframes(len(planes), arr, len(planes[0]), samplerate, _p(st, _intp), _p(ln, _intp), _p(ss, _intp), cap)
+    if n < 0:
+        raise SacError("sac_analyse_subframes failed (%d): %s" % (n, lib().sac_last_error().decode()))
+    return [(int(st[i]), int(ln[i]), int(ss[i])) for i in range(n)]
 
 
 def de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.15, entry="sac_de_run"):

@@ -827,6 +827,71 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
 }
 
 // =====================================================================================================================
+// adaptive frame split (Codec::Analyse / PushState, libsac.cpp:695-780; SparsePCM::Analyse, sparse.h:25-70)
+// =====================================================================================================================
+namespace {
+struct SubFrame { int state = -1, start = 0, length = 0; };        // Codec::tsub_frame (libsac.h:87-91)
+
+// SparsePCM::Analyse: ratio of the L1 norm of the values to the L1 norm of their rank distances among the used values
+double sparse_cost(const int32_t *buf, int n)
+{
+  int32_t minval = std::numeric_limits<int32_t>::max(), maxval = std::numeric_limits<int32_t>::min();
+  for (int i = 0; i < n; i++) { if (buf[i] > maxval) maxval = buf[i]; if (buf[i] < minval) minval = buf[i]; }
+  const int N = (int)((long long)maxval - (long long)minval + 1);
+  std::vector<int> used(N, 0), prefix(N + 1, 0);
+  for (int i = 0; i < n; i++) used[buf[i] - minval] = 1;
+  for (int i = 0; i < N; i++) prefix[i + 1] = prefix[i] + used[i];
+  double sum0 = 0, sum1 = 0;
+  for (int i = 0; i < n; i++) {
+    const int32_t val = buf[i];
+    int rank = 0;                                                     // val2rank_fast(val, p = 0)
+    if (val != 0) {
+      const int tidx = val - minval, pidx = 0 - minval;
+      if (val > 0) rank = prefix[tidx + 1] - prefix[std::clamp(pidx + 1, 0, N)];
+      else rank = prefix[tidx] - prefix[std::clamp(pidx, 0, N)];
+    }
+    sum0 += std::fabs((double)val);
+    sum1 += std::fabs((double)rank);
+  }
+  return sum1 > 0 ? sum0 / sum1 : 0;
+}
+
+void push_state(std::vector<SubFrame> &sub, SubFrame &cur, int min_len, int block_state = -1, int samples_block = 0)
+{
+  if (block_state == cur.state) cur.length += samples_block;
+  else {
+    if (cur.length < min_len && sub.size()) sub.back().length += cur.length;      // extend the previous sub-frame
+    else {
+      sub.push_back(cur);
+      if (samples_block) { cur.state = block_state; cur.start += cur.length; cur.length = samples_block; }
+    }
+  }
+}
+
+// blocks of `blocksamples` are classed sparse (rank-mapped cost ratio above 1.35) or not; runs of equal class form the
+// sub-frames, a short tail joins its predecessor
+std::vector<SubFrame> analyse_subframes(const std::vector<std::vector<int32_t>> &samples, int blocksamples, int min_len, int samples_read)
+{
+  std::vector<SubFrame> sub;
+  SubFrame cur;
+  int done = 0, nblock = 0;
+  while (done < samples_read) {
+    const int samples_block = std::min(blocksamples, samples_read - done);
+    double avg_cost = 0;
+    for (size_t ch = 0; ch < samples.size(); ch++) avg_cost += sparse_cost(samples[ch].data() + done, samples_block);
+    avg_cost /= (double)samples.size();
+    const int block_state = (avg_cost > 1.35);
+    if (nblock == 0) { cur.state = block_state; cur.length = samples_block; cur.start = 0; }
+    else push_state(sub, cur, min_len, block_state, samples_block);
+    done += samples_block;
+    nblock++;
+  }
+  if (cur.length) push_state(sub, cur, min_len);
+  return sub;
+}
+} // namespace
+
+// =====================================================================================================================
 // files
 // =====================================================================================================================
 static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out, sac_file_stats *st)
@@ -855,17 +920,25 @@ static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_
   const size_t pcm_bytes = (size_t)wi.numsamples * wi.blockalign;
   Md5 md5;
   md5.update(pcm, pcm_bytes);
-  const int nframes = (int)((wi.numsamples + (uint32_t)max_framesize - 1) / (uint32_t)max_framesize);
-  std::vector<std::vector<int32_t>> store((size_t)nframes * wi.nch);
-  std::vector<const int32_t *> ptrs((size_t)nframes * wi.nch);
-  std::vector<int> ns(nframes);
-  for (int f = 0; f < nframes; f++) {
-    const int first = f * max_framesize;
-    ns[f] = (int)std::min<uint32_t>((uint32_t)max_framesize, wi.numsamples - (uint32_t)first);
-    std::vector<std::vector<int32_t>> pl(wi.nch, std::vector<int32_t>(ns[f]));
-    wav_unpack(wi, pcm, first, ns[f], pl);
-    for (int ch = 0; ch < wi.nch; ch++) { store[(size_t)f * wi.nch + ch] = std::move(pl[ch]); ptrs[(size_t)f * wi.nch + ch] = store[(size_t)f * wi.nch + ch].data(); }
+  // reads of max_framesize samples, each split into sub-frames (Codec::EncodeFile, libsac.cpp:805-835)
+  std::vector<std::vector<int32_t>> store;
+  std::vector<int> ns;
+  for (uint32_t first = 0; first < wi.numsamples; first += (uint32_t)max_framesize) {
+    const int nread = (int)std::min<uint32_t>((uint32_t)max_framesize, wi.numsamples - first);
+    std::vector<std::vector<int32_t>> pl(wi.nch, std::vector<int32_t>(nread));
+    wav_unpack(wi, pcm, (int)first, nread, pl);
+    std::vector<SubFrame> sub;
+    if (cfg.adapt_block) sub = analyse_subframes(pl, wi.samplerate * 3, wi.samplerate * 3, nread);
+    else { SubFrame s; s.state = 0; s.start = 0; s.length = nread; sub.push_back(s); }
+    for (const SubFrame &s : sub) {
+      if (s.length <= 0) continue;
+      for (int ch = 0; ch < wi.nch; ch++) store.emplace_back(pl[ch].begin() + s.start, pl[ch].begin() + s.start + s.length);
+      ns.push_back(s.length);
+    }
   }
+  const int nframes = (int)ns.size();
+  std::vector<const int32_t *> ptrs((size_t)nframes * wi.nch);
+  for (size_t i = 0; i < ptrs.size(); i++) ptrs[i] = store[i].data();
   float prof[kProfileSize];
   for (int i = 0; i < kProfileSize; i++) prof[i] = kBaseProfile[i][2];
   if (nframes > 0) {
@@ -1021,6 +1094,20 @@ double sac_cma_run(int D, const double *xmin, const double *xmax, const double *
   } while (!s.done());
   if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);
   return s.best_cost();
+}
+
+int sac_analyse_subframes(int nch, const int32_t *const *planes, int numsamples, int samplerate, int *start, int *length, int *state, int cap)
+{
+  if (nch < 1 || nch > 2 || !planes || numsamples <= 0 || samplerate <= 0) { set_error("sac_analyse_subframes: bad argument"); return SAC_E_ARG; }
+  std::vector<std::vector<int32_t>> pl(nch);
+  for (int ch = 0; ch < nch; ch++) pl[ch].assign(planes[ch], planes[ch] + numsamples);
+  const std::vector<SubFrame> sub = analyse_subframes(pl, samplerate * 3, samplerate * 3, numsamples);
+  for (int i = 0; i < (int)sub.size() && i < cap; i++) {
+    if (start) start[i] = sub[i].start;
+    if (length) length[i] = sub[i].length;
+    if (state) state[i] = sub[i].state;
+  }
+  return (int)sub.size();
 }
 
 int sac_bitplane_encode(sac_engine *h, const int32_t *resid, int n, int *maxbpn_io, uint8_t *out, long long cap, long long *out_len)

@@ -139,3 +139,22 @@ def test_de_and_cma_drivers_match_reference_goldens():
         assert len(trace) == c["evals"], c
         assert sha(np.stack(trace)) == c["trace_sha1"], c
         assert best == c["best"] and sha(xb) == c["xbest_sha1"], c
+
+
+def test_adaptive_subframe_split_matches_the_reference_cli():
+    """Codec::Analyse (adaptive sub-frame split, SURVEY section 8 f-2, host part): for WAVs with sparse stretches the frame
+    lengths chosen per 20-s read equal those the UNMODIFIED reference CLI wrote (tests/golden/make_golden_split.py)"""
+    import json, sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_split import case_pcm
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_split.json")))
+    for c in g["cases"]:
+        pcm = case_pcm(c["nch"], c["sr"], c["secs"], c["seed"], [tuple(s) for s in c["sparse"]])
+        frames, maxf = [], 20 * c["sr"]
+        for first in range(0, len(pcm), maxf):
+            blk = pcm[first:first + maxf]
+            sub = sb.analyse_subframes([blk[:, ch] for ch in range(c["nch"])], c["sr"])
+            assert sum(l for _, l, _ in sub) == len(blk) and all(s == sum(x[1] for x in sub[:i]) for i, (s, _, _) in enumerate(sub))
+            frames += [l for _, l, _ in sub]
+        assert frames == c["frames"], (c["name"], frames, c["frames"])
