@@ -162,6 +162,57 @@ int ref_frame_get_encoded(void *hp, int ch, uint8_t *dst, int cap)
   return n;
 }
 
+// sparse-PCM side of a frame (libsac.cpp:214-298, map.cpp): maxbpn of the rank-mapped residuals; loading a coded block
+// back and running the reference's Decode() + Unpredict() on it
+int ref_frame_get_maxbpn_map(void *hp, int ch) { return static_cast<RefFrame *>(hp)->fc->framestats[ch].maxbpn_map; }
+void ref_frame_load_block(void *hp, int ch, const uint8_t *payload, int nbytes, int32_t mean, int32_t minval,
+                          int32_t maxval, int maxbpn, int enc_mapped)
+{
+  auto *h = static_cast<RefFrame *>(hp);
+  auto &st = h->fc->framestats[ch];
+  st.mean = mean; st.minval = minval; st.maxval = maxval; st.maxbpn = maxbpn; st.enc_mapped = enc_mapped != 0; st.blocksize = nbytes;
+  auto &b = h->fc->encoded[ch].GetBuf();
+  if ((int)b.size() < nbytes + 8) b.resize(nbytes + 8);
+  std::copy_n(payload, nbytes, b.begin());
+}
+void ref_frame_decode(void *hp, int n)
+{
+  auto *h = static_cast<RefFrame *>(hp);
+  h->fc->SetNumSamples(n);
+  h->fc->Decode();
+  h->fc->Unpredict();
+}
+int ref_frame_get_samples(void *hp, int ch, int32_t *dst)
+{
+  auto *h = static_cast<RefFrame *>(hp);
+  int n = h->fc->numsamples_;
+  std::copy_n(h->fc->samples[ch].begin(), n, dst);
+  return n;
+}
+// MapEncoder alone on the used-value map of `raw` (Remap::Analyse, map.cpp:126-157; MapEncoder::Encode, map.cpp:76-89)
+int ref_map_encode(const int32_t *raw, int n, uint8_t *out, int cap)
+{
+  Remap m; m.Reset();
+  std::vector<int32_t> tmp(raw, raw + n);
+  m.Analyse(tmp.data(), n);
+  BufIO buf;
+  RangeCoderSH rc(buf);
+  rc.Init();
+  MapEncoder me(rc, m.usedl, m.usedh);
+  me.Encode();
+  rc.Stop();
+  int nb = (int)buf.GetBufPos();
+  if (out && nb <= cap) std::copy_n(buf.GetBuf().begin(), nb, out);
+  return nb;
+}
+void ref_remap(const int32_t *raw, int nraw, const int32_t *pred, const int32_t *err, int n, int unmap, int32_t *out)
+{
+  Remap m; m.Reset();
+  std::vector<int32_t> tmp(raw, raw + nraw);
+  m.Analyse(tmp.data(), nraw);
+  for (int i = 0; i < n; i++) out[i] = unmap ? m.Unmap(pred[i], err[i]) : m.Map(pred[i], err[i]);
+}
+
 // ---- cost functions (src/libsac/cost.h) ----------------------------------------------------------------------
 double ref_cost(int kind, const int32_t *buf, int n)
 {

@@ -573,8 +573,13 @@ int predict_frame(int nch, const int32_t *const *planes, int from, int n, const 
   return pr.bad() ? 1 : 0;
 }
 
-int unpredict_frame(int nch, int n, const float *prof, const int32_t *mm, const int32_t *const *err, int32_t *const *dst)
+struct Remap;
+int32_t remap_unmap(const Remap *m, int32_t pred, int32_t merr);
+// maps[ch] != nullptr: the channel's residuals are rank-mapped (libsac.cpp:157-160), mean[ch] re-bases the prediction
+int unpredict_frame(int nch, int n, const float *prof, const int32_t *mm, const int32_t *const *err, int32_t *const *dst,
+                    const Remap *const *maps = nullptr, const int32_t *mean = nullptr)
 {
+  auto residual = [&](int ch, int32_t pi, int32_t e) { return (maps && maps[ch]) ? remap_unmap(maps[ch], pi + mean[ch], e) : e; };
   Param param = set_param(prof, 1);
   int32_t mm4[4] = {mm[0], mm[1], nch == 2 ? mm[2] : mm[0], nch == 2 ? mm[3] : mm[1]};
   Predictor pr(param, mm4);
@@ -583,7 +588,7 @@ int unpredict_frame(int nch, int n, const float *prof, const int32_t *mm, const 
     for (int idx = 0; idx < n; idx++) {
       pr.fill0(d, idx, d, idx);
       const int32_t pi = round_clamp(pr.predict(0), mm[0], mm[1]);
-      d[idx] = pi + err[0][idx];
+      d[idx] = pi + residual(0, pi, err[0][idx]);
       pr.update(0, d[idx]);
     }
   } else {
@@ -594,14 +599,14 @@ int unpredict_frame(int nch, int n, const float *prof, const int32_t *mm, const 
       if (idx0 < n) {
         pr.fill0(d0, idx0, d1, idx1);
         const int32_t pi = round_clamp(pr.predict(0), mm[2 * ch0], mm[2 * ch0 + 1]);
-        d0[idx0] = pi + err[ch0][idx0];
+        d0[idx0] = pi + residual(ch0, pi, err[ch0][idx0]);
         pr.update(0, d0[idx0]);
         idx0++;
       }
       if (idx0 >= param.nS1) {
         pr.fill1(d0, d1, idx1, n);
         const int32_t pi = round_clamp(pr.predict(1), mm[2 * ch1], mm[2 * ch1 + 1]);
-        d1[idx1] = pi + err[ch1][idx1];
+        d1[idx1] = pi + residual(ch1, pi, err[ch1][idx1]);
         pr.update(1, d1[idx1]);
         idx1++;
       }
@@ -685,13 +690,14 @@ struct MixLogistic {                                                // mixer.h:5
     }
   }
 };
-struct Ssenl {                                                      // sse.h:84-125, N=15
+template <int N> struct SsenlT {                                    // sse.h:84-125 (SSENL<N>)
   int tscale, xscale, lb = 0, p_quant = 0;
-  Counter16 Map[2][16];
-  Ssenl()
+  Counter16 Map[2][N + 1];
+  SsenlT()
   {
-    tscale = T().tmax; xscale = (2 * tscale) / 14;
-    for (int i = 0; i <= 15; i++) { int x = T().Inv(i * xscale - tscale); Map[0][i].p1 = x; Map[1][i].p1 = x; }
+    tscale = T().tmax; xscale = (2 * tscale) / (N - 1);
+    if (xscale == 0) xscale = 1;
+    for (int i = 0; i <= N; i++) { int x = T().Inv(i * xscale - tscale); Map[0][i].p1 = x; Map[1][i].p1 = x; }
   }
   int Predict(int p1)
   {
@@ -709,6 +715,7 @@ struct Ssenl {                                                      // sse.h:84-
     lb = bit;
   }
 };
+typedef SsenlT<15> Ssenl;
 
 // ---------------------------------------------------------------------------------------------------------------
 // range coder (ref model/range.cpp:54-92)
@@ -747,6 +754,122 @@ struct RangeDec {
     if (bit) { range -= rnew; code -= rnew; } else range = rnew;
     while (range < 0x01000000U) { range <<= 8; code = (code << 8) + get(); }
     return bit;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// sparse PCM: which of the 2 x 32768 magnitudes occur (Remap, ref libsac/map.h:36-49, map.cpp:104-202) and their
+// context-coded transmission (MapEncoder, map.h:10-34, map.cpp:3-102)
+// ---------------------------------------------------------------------------------------------------------------
+struct Remap {
+  static const int scale = 1 << 15;
+  int vmin = 0, vmax = 0;
+  std::vector<uint8_t> usedl, usedh;
+  Remap() : usedl(scale + 1, 0), usedh(scale + 1, 0) {}
+  void Analyse(const int32_t *src, int n)                              // map.cpp:126-157 (raw samples, before mean removal)
+  {
+    for (int i = 0; i < n; i++) {
+      int val = src[i];
+      if (val > 0) { if (val <= scale) { if (val > vmax) vmax = val; usedh[val] = 1; } }
+      else if (val < 0) { val = -val; if (val <= scale) { if (val > vmin) vmin = val; usedl[val] = 1; } }
+    }
+  }
+  bool isUsed(int val) const                                           // map.cpp:159-166
+  {
+    if (val > scale) return false;
+    if (val < -scale) return false;
+    if (val > 0) return usedh[val];
+    if (val < 0) return usedl[-val];
+    return true;
+  }
+  int32_t Map(int32_t pred, int32_t err) const                         // map.cpp:175-186
+  {
+    int sg = 1;
+    if (err == 0) return 0;
+    if (err < 0) { err = -err; sg = -1; }
+    int merr = 0;
+    for (int i = 1; i <= err; i++) if (isUsed(pred + (sg * i))) merr++;
+    return sg * merr;
+  }
+  int32_t Unmap(int32_t pred, int32_t merr) const                      // map.cpp:188-202
+  {
+    int sg = 1;
+    if (merr == 0) return 0;
+    if (merr < 0) { merr = -merr; sg = -1; }
+    int err = 1, terr = 0;
+    while (1) {
+      if (isUsed(pred + (sg * err))) terr++;
+      if (terr == merr) break;
+      err++;
+    }
+    return sg * err;
+  }
+};
+
+int32_t remap_unmap(const Remap *m, int32_t pred, int32_t merr) { return m->Unmap(pred, merr); }
+
+struct MapCoder {
+  Counter16 cnt[24], cctx[256];
+  Counter16 *pc1 = nullptr, *pc2 = nullptr, *pc3 = nullptr, *pc4 = nullptr, *px = nullptr;
+  MixLogistic mixl[4], mixh[4], finalmix, *mix = nullptr;
+  SsenlT<32> sse0;                                                      // only sse[0] is ever addressed (map.cpp:83-99)
+  std::vector<uint8_t> &ul, &uh;
+  MapCoder(std::vector<uint8_t> &usedl, std::vector<uint8_t> &usedh) : ul(usedl), uh(usedh)
+  {
+    for (auto &m : mixl) m.n = 5;
+    for (auto &m : mixh) m.n = 5;
+    finalmix.n = 2;
+  }
+  int PredictLow(int i)                                                // map.cpp:9-29
+  {
+    const int ctx1 = ul[i - 1], ctx2 = uh[i - 1], ctx3 = i > 1 ? ul[i - 2] : 0;
+    pc1 = &cnt[ctx1]; pc2 = &cnt[2 + ctx2]; pc3 = &cnt[4 + (ctx1 << 1) + ctx3]; pc4 = &cnt[8 + (ctx1 << 1) + ctx2];
+    int sctx = ul[i - 1];
+    if (i > 1) sctx += (ul[i - 2] << 1);
+    if (i > 2) sctx += (ul[i - 3] << 2);
+    if (i > 3) sctx += (ul[i - 4] << 3);
+    px = &cctx[sctx];
+    mix = &mixl[ctx1 + (ctx3 << 1)];
+    const int p[5] = {pc1->p1, pc2->p1, pc3->p1, pc4->p1, px->p1};
+    return mix->Predict(p);
+  }
+  int PredictHigh(int i)                                               // map.cpp:31-52
+  {
+    const int ctx1 = uh[i - 1], ctx2 = ul[i], ctx3 = i > 1 ? uh[i - 2] : 0;
+    pc1 = &cnt[12 + ctx1]; pc2 = &cnt[12 + 2 + ctx2]; pc3 = &cnt[12 + 4 + (ctx1 << 1) + ctx3]; pc4 = &cnt[12 + 8 + (ctx1 << 1) + ctx2];
+    int sctx = uh[i - 1];
+    if (i > 1) sctx += (uh[i - 2] << 1);
+    if (i > 2) sctx += (uh[i - 3] << 2);
+    if (i > 3) sctx += (uh[i - 4] << 3);
+    px = &cctx[32 + sctx];
+    mix = &mixh[ctx1 + (ctx3 << 1)];
+    const int p[5] = {pc1->p1, pc2->p1, pc3->p1, pc4->p1, px->p1};
+    return mix->Predict(p);
+  }
+  void Update(int bit)                                                 // map.cpp:54-62
+  {
+    pc1->update(bit, 500); pc2->update(bit, 500); pc3->update(bit, 500); pc4->update(bit, 500); px->update(bit, 500);
+    mix->Update(bit, 1000);
+  }
+  int PredictSSE(int p1) { const int vp[2] = {sse0.Predict(p1), p1}; return finalmix.Predict(vp); }
+  void UpdateSSE(int bit) { sse0.Update(bit, 300); finalmix.Update(bit, 500); }
+  void Encode(RangeEnc &rc)                                            // map.cpp:76-89
+  {
+    for (int i = 1; i <= 1 << 15; i++) {
+      int bit = ul[i];
+      rc.Encode(PredictSSE(PredictLow(i)), bit); Update(bit); UpdateSSE(bit);
+      bit = uh[i];
+      rc.Encode(PredictSSE(PredictHigh(i)), bit); Update(bit); UpdateSSE(bit);
+    }
+  }
+  void Decode(RangeDec &rc)                                            // map.cpp:91-102
+  {
+    for (int i = 1; i <= 1 << 15; i++) {
+      int bit = rc.Decode(PredictSSE(PredictLow(i)));
+      Update(bit); ul[i] = bit; UpdateSSE(bit);
+      bit = rc.Decode(PredictSSE(PredictHigh(i)));
+      Update(bit); uh[i] = bit; UpdateSSE(bit);
+    }
   }
 };
 
@@ -894,12 +1017,26 @@ struct Bitplane {
   }
 };
 
-std::vector<uint8_t> bitplane_encode(const int32_t *ubuf, int n, int maxbpn)
+void bitplane_encode_into(RangeEnc &rc, const int32_t *ubuf, int n, int maxbpn)
 {
   std::vector<int32_t> tmp(ubuf, ubuf + n);
-  RangeEnc rc;
   Bitplane bc(maxbpn, n);
   bc.Run([&](int p, int bit) { rc.Encode(p, bit); return bit; }, tmp.data(), false);
+}
+std::vector<uint8_t> bitplane_encode(const int32_t *ubuf, int n, int maxbpn)
+{
+  RangeEnc rc;
+  bitplane_encode_into(rc, ubuf, n, maxbpn);
+  rc.Stop();
+  return rc.out;
+}
+// EncodeMonoFrame_Mapped (libsac.cpp:214-228): the used-value map, then the rank-mapped residuals, ONE range coder
+std::vector<uint8_t> mapped_encode(Remap &map, const int32_t *ubuf_map, int n, int maxbpn_map)
+{
+  RangeEnc rc;
+  MapCoder me(map.usedl, map.usedh);
+  me.Encode(rc);
+  bitplane_encode_into(rc, ubuf_map, n, maxbpn_map);
   rc.Stop();
   return rc.out;
 }
@@ -1081,10 +1218,11 @@ double saco_dds_run(int ndim, const double *xmin, const double *xmax, const doub
   return dds_run(ndim, xmin, xmax, xstart, nfunc_max, num_threads, sigma_init, cb, user, xbest);
 }
 
-// ref libsac/libsac.cpp:443-479 (Predict), :365-427 (Optimize), :429-441 (S2U), :201-212,:253-278 (Encode, sparse-pcm
-// path not restated: it never triggers below ratio 1.05), :507-578 (WriteEncoded)
-int saco_encode_frame(int nch, int n, const int32_t *s0_in, const int32_t *s1_in, float *profile_io, const int *cfg,
-                      uint8_t *out, int cap)
+// ref libsac/libsac.cpp:443-479 (Predict), :365-427 (Optimize), :429-441 (S2U), :201-278 (Encode incl. the sparse-pcm
+// choice: rank-mapped residuals when the L1 ratio exceeds 1.05 AND the mapped record is smaller), :507-578 (WriteEncoded)
+// mapped_out[ch] (optional) receives 1 where the channel was coded rank-mapped.
+int saco_encode_frame2(int nch, int n, const int32_t *s0_in, const int32_t *s1_in, float *profile_io, const int *cfg,
+                       int sparse_pcm, uint8_t *out, int cap, int *mapped_out)
 {
   const int optimize = cfg[0]; const double fraction = cfg[1] / 1e6; const int maxnfunc = cfg[2], nthreads = cfg[3];
   const double sigma = cfg[4] / 1e6; const int optk = cfg[5], cost_kind = cfg[6], framesize = cfg[7];
@@ -1092,7 +1230,9 @@ int saco_encode_frame(int nch, int n, const int32_t *s0_in, const int32_t *s1_in
   s[0].assign(s0_in, s0_in + n);
   if (nch == 2) s[1].assign(s1_in, s1_in + n);
   int32_t mean[2] = {0, 0}, mm[4] = {0, 0, 0, 0};
-  for (int ch = 0; ch < nch; ch++) {                                // libsac.cpp:626-651, 452-458
+  Remap maps[2];
+  for (int ch = 0; ch < nch; ch++) {                                // libsac.cpp:626-651, 448-458
+    if (sparse_pcm) maps[ch].Analyse(s[ch].data(), n);              // on the raw samples, before the mean is removed
     int64_t sum = 0;
     int32_t mn = std::numeric_limits<int32_t>::max(), mx = std::numeric_limits<int32_t>::min();
     for (int i = 0; i < n; i++) { sum += s[ch][i]; mx = std::max(mx, s[ch][i]); mn = std::min(mn, s[ch][i]); }
@@ -1137,14 +1277,56 @@ int saco_encode_frame(int nch, int n, const int32_t *s0_in, const int32_t *s1_in
     for (int i = 0; i < n; i++) { u[i] = S2U(e[ch][i]); emax = std::max(emax, u[i]); }
     const int maxbpn = iLog2(emax);
     std::vector<uint8_t> payload = bitplane_encode(u.data(), n, maxbpn);
+    int flag = maxbpn;
+    if (mapped_out) mapped_out[ch] = 0;
+    if (sparse_pcm) {                                               // CalcRemapError, libsac.cpp:230-251, 259-276
+      std::vector<int32_t> em(n), um(n); int32_t emax_map = 0;
+      for (int i = 0; i < n; i++) {
+        const int32_t pred = (s[ch][i] - e[ch][i]) + mean[ch];      // pred[ch][i] = pi + mean (libsac.cpp:107)
+        em[i] = maps[ch].Map(pred, e[ch][i]); um[i] = S2U(em[i]); emax_map = std::max(emax_map, um[i]);
+      }
+      const int maxbpn_map = iLog2(emax_map);
+      const double ent1 = cost_calc(SACO_COST_L1, e[ch].data(), n), ent2 = cost_calc(SACO_COST_L1, em.data(), n);
+      const double r = ent2 != 0.0 ? ent1 / ent2 : 1.0;
+      if (r > 1.05) {
+        std::vector<uint8_t> pm = mapped_encode(maps[ch], um.data(), n, maxbpn_map);
+        if (pm.size() < payload.size()) { payload.swap(pm); flag = (1 << 9) | maxbpn_map; if (mapped_out) mapped_out[ch] = 1; }
+      }
+    }
     uint8_t hdr[18];
     put32(hdr, (uint32_t)payload.size()); put32(hdr + 4, (uint32_t)mean[ch]); put32(hdr + 8, (uint32_t)mm[2 * ch]);
-    put32(hdr + 12, (uint32_t)mm[2 * ch + 1]); hdr[16] = maxbpn & 0xff; hdr[17] = 0;
+    put32(hdr + 12, (uint32_t)mm[2 * ch + 1]); hdr[16] = flag & 0xff; hdr[17] = (flag >> 8) & 0xff;
     rec.insert(rec.end(), hdr, hdr + 18);
     rec.insert(rec.end(), payload.begin(), payload.end());
   }
   if (out && (int)rec.size() <= cap) std::copy(rec.begin(), rec.end(), out);
   return (int)rec.size();
+}
+
+int saco_encode_frame(int nch, int n, const int32_t *s0_in, const int32_t *s1_in, float *profile_io, const int *cfg,
+                      uint8_t *out, int cap)
+{
+  return saco_encode_frame2(nch, n, s0_in, s1_in, profile_io, cfg, 1 /* FrameCoder::tsac_cfg default, libsac.h:34 */, out, cap, nullptr);
+}
+
+// used-value map alone: Remap::Analyse + MapEncoder::Encode + Stop (map.cpp:76-89, 126-157) -> bytes; and back
+int saco_map_encode(const int32_t *raw, int n, uint8_t *out, int cap)
+{
+  Remap m; m.Analyse(raw, n);
+  RangeEnc rc; MapCoder me(m.usedl, m.usedh); me.Encode(rc); rc.Stop();
+  if (out && (int)rc.out.size() <= cap) std::copy(rc.out.begin(), rc.out.end(), out);
+  return (int)rc.out.size();
+}
+void saco_map_decode(const uint8_t *in, int nbytes, uint8_t *usedl /*[32769]*/, uint8_t *usedh /*[32769]*/)
+{
+  Remap m; RangeDec rd(in, nbytes); MapCoder me(m.usedl, m.usedh); me.Decode(rd);
+  std::copy(m.usedl.begin(), m.usedl.end(), usedl); std::copy(m.usedh.begin(), m.usedh.end(), usedh);
+}
+// Remap::Map / Unmap element-wise against the map of `raw` (map.cpp:175-202)
+void saco_remap(const int32_t *raw, int nraw, const int32_t *pred, const int32_t *err, int n, int unmap, int32_t *out)
+{
+  Remap m; m.Analyse(raw, nraw);
+  for (int i = 0; i < n; i++) out[i] = unmap ? m.Unmap(pred[i], err[i]) : m.Map(pred[i], err[i]);
 }
 
 // ref libsac/libsac.cpp:580-593 (ReadEncoded), :280-298 (DecodeMonoFrame), :144-199 (UnpredictFrame)
@@ -1157,18 +1339,25 @@ int saco_decode_frame(int nch, const uint8_t *in, int len, int32_t *s0, int32_t 
   for (int i = 0; i < 58; i++) { uint32_t ix = get32(in + pos); std::memcpy(&prof[i], &ix, 4); pos += 4; }
   std::vector<int32_t> e[2];
   int32_t mean[2] = {0, 0}, mm[4] = {0, 0, 0, 0};
+  Remap maps[2]; bool mapped[2] = {false, false};
   for (int ch = 0; ch < nch; ch++) {
     const int blocksize = (int)get32(in + pos);
     mean[ch] = (int32_t)get32(in + pos + 4); mm[2 * ch] = (int32_t)get32(in + pos + 8); mm[2 * ch + 1] = (int32_t)get32(in + pos + 12);
-    const int maxbpn = in[pos + 16];
+    const int flag = in[pos + 16] | (in[pos + 17] << 8);             // ReadBlockHeader, libsac.cpp:551-564
+    const int maxbpn = flag & 0xff;
+    mapped[ch] = (flag >> 9) != 0;
     pos += 18;
     e[ch].resize(n);
-    saco_bitplane_decode(in + pos, blocksize, n, maxbpn, e[ch].data());
+    RangeDec rd(in + pos, blocksize);
+    if (mapped[ch]) { MapCoder me(maps[ch].usedl, maps[ch].usedh); me.Decode(rd); }   // DecodeMonoFrame, libsac.cpp:280-298
+    Bitplane bc(maxbpn, n);
+    bc.Run([&](int p, int) { return rd.Decode(p); }, e[ch].data(), true);
     pos += blocksize;
   }
   const int32_t *err[2] = {e[0].data(), e[1].data()};
   int32_t *dst[2] = {s0, s1};
-  unpredict_frame(nch, n, prof, mm, err, dst);
+  const Remap *mp[2] = {mapped[0] ? &maps[0] : nullptr, mapped[1] ? &maps[1] : nullptr};
+  unpredict_frame(nch, n, prof, mm, err, dst, mp, mean);
   for (int ch = 0; ch < nch; ch++)
     if (mean[ch] != 0) for (int i = 0; i < n; i++) dst[ch][i] += mean[ch];
   *n_out = n;

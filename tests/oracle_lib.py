@@ -73,6 +73,11 @@ def ref_lib(nc=True):
               "ref_frame_set_profile", "ref_frame_get_profile", "ref_frame_predict_window", "ref_frame_predict",
               "ref_frame_encode", "ref_frame_get_error", "ref_frame_get_encoded", "ref_frame_set_mt"):
         getattr(lib, f).argtypes = None
+    if hasattr(lib, "ref_frame_load_block"):
+        lib.ref_frame_load_block.argtypes = [C.c_void_p, C.c_int, _u8p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int, C.c_int]
+        lib.ref_frame_decode.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_frame_get_samples.argtypes = [C.c_void_p, C.c_int, _i32p]
+        lib.ref_frame_get_maxbpn_map.argtypes = [C.c_void_p, C.c_int]
     return lib
 
 
@@ -224,6 +229,24 @@ class RefFrame:
         nb = self.lib.ref_frame_get_encoded(self.h, ch, None, 0)
         out = np.zeros(nb, np.uint8)
         self.lib.ref_frame_get_encoded(self.h, ch, _p(out, _u8p), nb)
+        return out
+
+    def maxbpn_map(self, ch):
+        return int(self.lib.ref_frame_get_maxbpn_map(self.h, ch))
+
+    def decode_blocks(self, n, profile, blocks):
+        """blocks: per channel (payload u8, mean, min, max, maxbpn, mapped) -> the reference's Decode()+Unpredict() samples"""
+        prof = np.ascontiguousarray(profile, np.float32)
+        self.lib.ref_frame_set_profile(self.h, _p(prof, _f32p))
+        for ch, (pay, mean, mn, mx, bpn, mapped) in enumerate(blocks):
+            pay = np.ascontiguousarray(pay, np.uint8)
+            self.lib.ref_frame_load_block(self.h, ch, _p(pay, _u8p), len(pay), int(mean), int(mn), int(mx), int(bpn), int(mapped))
+        self.lib.ref_frame_decode(self.h, n)
+        out = []
+        for ch in range(self.nch):
+            d = np.zeros(n, np.int32)
+            self.lib.ref_frame_get_samples(self.h, ch, _p(d, _i32p))
+            out.append(d)
         return out
 
     def __del__(self):

@@ -1,6 +1,7 @@
 """Pins oracle/sac_oracle.cpp (reference order, libm) against the golden vectors generated from the reference's own
 classes (tests/golden/make_golden.py) and, where oracle/_ref is present, against the reference live. CPU only."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -10,6 +11,7 @@ from helpers import case_planes, case_profile, sha, special_streams
 from synth_wav import synth_pcm
 
 REF = (ol.ORDER_REF, ol.MATH_LIBM)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_base_profile(golden):
@@ -173,3 +175,77 @@ def test_b200_order_is_statistically_the_reference(golden):
         if c["k"] == 1:
             s = ol.oracle_unpredict(e, mm, prof, ol.ORDER_B200, ol.MATH_CANON)
             assert all(np.array_equal(s[ch][:c["n"]], planes[ch][c["frm"]:c["frm"] + c["n"]]) for ch in range(c["nch"])) or c["frm"] != 0
+
+
+def _sparse_golden():
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_sparse import sparse_pcm
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "golden_sparse.json"))), sparse_pcm
+
+
+def test_sparse_pcm_map_matches_reference():
+    """Remap::Analyse/Map/Unmap and MapEncoder (map.cpp) vs the restatement: coded map bytes, rank-mapped residuals, and
+    the decoded map equals the analysed one (tests/golden/make_golden_sparse.py)"""
+    g, sparse_pcm = _sparse_golden()
+    lib = ol.oracle()
+    lib.saco_set_modes(*REF)
+    for c in g["map"]:
+        raw = np.ascontiguousarray(sparse_pcm(c["kind"], c["secs"], c["nch"], c["seed"])[:, 0])
+        buf = np.zeros(1 << 16, np.uint8)
+        nb = lib.saco_map_encode(ol._p(raw, ol._i32p), len(raw), ol._p(buf, ol._u8p), len(buf))
+        assert nb == c["nbytes"] and sha(buf[:nb]) == c["sha1"], c["kind"]
+        ul = np.zeros(32769, np.uint8); uh = np.zeros(32769, np.uint8)
+        lib.saco_map_decode(ol._p(buf, ol._u8p), nb, ol._p(ul, ol._u8p), ol._p(uh, ol._u8p))
+        pos = np.unique(raw[(raw > 0)]); neg = np.unique(-raw[raw < 0])
+        wl = np.zeros(32769, np.uint8); wh = np.zeros(32769, np.uint8)
+        wh[pos[pos <= 32768]] = 1; wl[neg[neg <= 32768]] = 1
+        assert np.array_equal(ul, wl) and np.array_equal(uh, wh), c["kind"]
+        rng = np.random.default_rng(c["seed"])
+        n = c["n"]
+        pred = rng.integers(-33000, 33000, n).astype(np.int32)
+        err = (rng.laplace(0, 90, n)).astype(np.int32)
+        m = np.zeros(n, np.int32); um = np.zeros(n, np.int32)
+        lib.saco_remap(ol._p(raw, ol._i32p), len(raw), ol._p(pred, ol._i32p), ol._p(err, ol._i32p), n, 0, ol._p(m, ol._i32p))
+        lib.saco_remap(ol._p(raw, ol._i32p), len(raw), ol._p(pred, ol._i32p), ol._p(m, ol._i32p), n, 1, ol._p(um, ol._i32p))
+        assert sha(m) == c["map_sha1"] and sha(um) == c["unmap_sha1"], c["kind"]
+
+
+def test_sparse_pcm_frame_records_match_reference():
+    """FrameCoder::EncodeMonoFrame with sparse_pcm=1 (the CLI default): which channels are coded rank-mapped, the block
+    header flag (1<<9 | maxbpn_map) and the payload bytes; the restated decoder (MapEncoder::Decode + Unmap) inverts them"""
+    g, sparse_pcm = _sparse_golden()
+    lib = ol.oracle()
+    lib.saco_set_modes(*REF)
+    _, _, vdef = ol.base_profile()
+    for c in g["frame"]:
+        pcm = sparse_pcm(c["kind"], c["secs"], c["nch"], c["seed"])
+        s = [np.ascontiguousarray(pcm[:, ch]) for ch in range(c["nch"])]
+        cfg = (C.c_int * 8)(0, 0, 0, 0, 200000, 4, 2, 20 * 44100)
+        prof = vdef.copy()
+        out = np.zeros(8 * len(s[0]) + 4096, np.uint8)
+        mapped = (C.c_int * 2)(0, 0)
+        nb = lib.saco_encode_frame2(c["nch"], len(s[0]), ol._p(s[0], ol._i32p), ol._p(s[1], ol._i32p) if c["nch"] > 1 else None,
+                                    ol._p(prof, ol._f32p), cfg, 1, ol._p(out, ol._u8p), len(out), mapped)
+        rec = out[:nb]
+        pos = 4 + 58 * 4
+        for ch in range(c["nch"]):
+            st = c["stats"][ch]
+            bs = int.from_bytes(rec[pos:pos + 4].tobytes(), "little")
+            mean, mn, mx = np.frombuffer(rec[pos + 4:pos + 16].tobytes(), "<i4")
+            flag = int(rec[pos + 16]) | (int(rec[pos + 17]) << 8)
+            assert [int(mean), int(mn), int(mx)] == st[:3] and mapped[ch] == st[5], c["name"]
+            assert flag == (((1 << 9) | c["maxbpn_map"][ch]) if st[5] else st[3]), c["name"]
+            assert bs == c["payload_len"][ch] and sha(rec[pos + 18:pos + 18 + bs]) == c["payload_sha1"][ch], c["name"]
+            pos += 18 + bs
+        assert pos == nb
+        d = [np.zeros(len(s[0]), np.int32) for _ in range(c["nch"])]
+        n_out = C.c_int(0)
+        used = lib.saco_decode_frame(c["nch"], ol._p(rec, ol._u8p), nb, ol._p(d[0], ol._i32p), ol._p(d[1], ol._i32p) if c["nch"] > 1 else None,
+                                     C.byref(n_out))
+        assert used == nb and all(np.array_equal(a, b) for a, b in zip(d, s)), c["name"]
+        # with --sparse-pcm=0 nothing is mapped
+        nb0 = lib.saco_encode_frame2(c["nch"], len(s[0]), ol._p(s[0], ol._i32p), ol._p(s[1], ol._i32p) if c["nch"] > 1 else None,
+                                     ol._p(prof, ol._f32p), cfg, 0, ol._p(out, ol._u8p), len(out), mapped)
+        assert list(mapped)[:c["nch"]] == [0] * c["nch"] and (nb0 > nb) == any(x[5] for x in c["stats"])
