@@ -128,7 +128,7 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
   int cost_kind;                /* SAC_COST_* */
   int reset;                    /* --opt-reset: every frame starts from the base profile */
   int zero_mean;                /* 1 */
-  int sparse_pcm;               /* accepted for CLI compatibility; rank-mapped coding of sparse frames is not implemented (frames are coded unmapped) */
+  int sparse_pcm;               /* 1 (default): a channel whose sample values are sparse is also coded as rank distances among the used values behind the coded value map, and the shorter record is kept (libsac.cpp:253-278, map.cpp) */
   int max_framelen;             /* seconds (20) */
   int adapt_block;              /* adaptive sub-frame split of every max_framelen read (Codec::Analyse, libsac.cpp:726-780) */
   int frame_parallel;           /* B200 extension (implies --opt-reset semantics): 1 = all frames of a call share each generation's launches,

@@ -14,6 +14,7 @@
 // The decoder cannot look ahead (contexts depend on bits decoded in the current plane) and evaluates each
 // decision cooperatively across one warp instead.
 #include "bitplane.h"
+#include "model_dev.cuh"
 #include "sac_canon_math.h"
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -23,7 +24,6 @@ namespace sacb {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int PBITS = 15, PSCALE = 1 << 15, PSCALEm = PSCALE - 1;
 constexpr int kTScale = 2662, kXScale = 380;                       // SSENL<15>: tscale=myDomain.max, xscale=2*tscale/14
 constexpr int kLimP = 150, kLimSig = 300, kLimRef = 150;           // vle.h:43-45
 constexpr int kRateRef = 800, kRateSig = 700, kRateSse = 250, kRateSseMix = 250;   // vle.h:46-49
@@ -43,23 +43,6 @@ struct BpState {
   uint32_t sse_lb[160];
 };
 
-__device__ __forceinline__ int idiv_s(int val, int s) { return val < 0 ? -(((-val) + (1 << (s - 1))) >> s) : (val + (1 << (s - 1))) >> s; }
-__device__ __forceinline__ int idiv_s64(long long val, int s)
-{
-  return (int)(val < 0 ? -(((-val) + (1LL << (s - 1))) >> s) : (val + (1LL << (s - 1))) >> s);
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-struct Tables { const int16_t *stretch; const int16_t *squash; const uint16_t *laplace; int lap_bits; };
-
-// stretch / squash point into the CTA's shared-memory copies (stage_tables): they sit on the serial chain of every decision
-__device__ __forceinline__ int stretch(const Tables &T, int p) { return T.stretch[p]; }
-__device__ __forceinline__ int squash(const Tables &T, int x)
-{
-  if (x < -2047) return 1;
-  if (x > 2047) return PSCALEm;
-  return T.squash[x + 2047];
-}
 
 // LinearCounterLimit::update (counter.h:58-68)
 __device__ __forceinline__ uint32_t counter_upd(uint32_t c, int bit, int limit)
@@ -70,12 +53,6 @@ __device__ __forceinline__ uint32_t counter_upd(uint32_t c, int bit, int limit)
   const int dp = bit ? ((PSCALE - p1) * dv) >> PBITS : -((p1 * dv) >> PBITS);
   p1 = clampi(p1 + dp, 1, PSCALEm);
   return (uint32_t)p1 | ((uint32_t)cnt << 16);
-}
-// LinearCounter16::update(bit, L) (counter.h:31-37)
-__device__ __forceinline__ int counter16_upd(int p1, int bit, int L)
-{
-  const int err = (bit << PBITS) - p1;
-  return clampi(p1 + idiv_s(L * err, PBITS), 1, PSCALEm);
 }
 
 // BitplaneCoder::PredictLaplace (vle.cpp:70-79) in canonical math
@@ -92,38 +69,6 @@ __device__ __forceinline__ int laplace_p(const Tables &T, uint32_t avg_sum, int 
 {
   if (bpn <= T.lap_bits - 1 && avg_sum < (1u << T.lap_bits)) return __ldg(T.laplace + ((size_t)bpn << T.lap_bits) + avg_sum);
   return laplace_calc(avg_sum, bpn);
-}
-
-// the adaptive chain for one binary decision; all lanes execute it with identical operands
-struct Coder {
-  uint32_t range, ffnum, cache;
-  unsigned long long lowc;
-  long long nbytes;
-  uint8_t *out;
-};
-
-template <int MODE /*0 cost, 1 encode*/>
-__device__ __forceinline__ void shift_low(Coder &rc, int lane)
-{
-  if (MODE == 1) {
-    const uint32_t carry = (uint32_t)(rc.lowc >> 32), low = (uint32_t)rc.lowc;
-    if (low < 0xFF000000u || carry) {
-      if (lane == 0) rc.out[rc.nbytes] = (uint8_t)(rc.cache + carry);
-      rc.nbytes++;
-      for (; rc.ffnum != 0; rc.ffnum--) { if (lane == 0) rc.out[rc.nbytes] = (uint8_t)(carry - 1); rc.nbytes++; }
-      rc.cache = low >> 24;
-    } else rc.ffnum++;
-    rc.lowc = (unsigned long long)(uint32_t)(low << 8);
-  } else {
-    rc.nbytes++;                                                   // every ShiftLow eventually emits exactly one byte
-  }
-}
-template <int MODE>
-__device__ __forceinline__ void rc_encode(Coder &rc, int p1, int bit, int lane)
-{
-  const uint32_t rnew = __umulhi(rc.range, (uint32_t)(PSCALE - p1) << (32 - PBITS));   // range.h:23
-  if (bit) { rc.range -= rnew; if (MODE == 1) rc.lowc += rnew; } else rc.range = rnew;
-  while (rc.range < 0x01000000u) { rc.range <<= 8; shift_low<MODE>(rc, lane); }
 }
 
 struct Decision {                                                  // unpacked per-sample record
@@ -328,6 +273,7 @@ __global__ void __launch_bounds__(kPipeThreads * kPipeStreams) bitplane_pipe_ker
   const int tid = threadIdx.x - sidx * kPipeThreads, lane = tid & 31, warp = tid >> 5;
   if (job >= njobs) return;
   const BpJob J = jobs[job];
+  if (J.rc_init && !J.rc_init->go) return;                         // mapped record not wanted (whole stream leaves, before any stream barrier)
   const int sbar = 1 + sidx;                                       // named barrier of this stream
   const int n = J.n;
   int32_t *u = J.buf;
@@ -605,6 +551,10 @@ __global__ void __launch_bounds__(kPipeThreads * kPipeStreams) bitplane_pipe_ker
     // ================================ W4: final mixer + coder =======================================================
     Coder rc;
     rc.range = 0xFFFFFFFFu; rc.ffnum = 0; rc.cache = 0; rc.lowc = 0; rc.nbytes = 0; rc.out = J.out;
+    if (J.rc_init) {                                               // the map coder's bytes are already in J.out[0, nbytes)
+      const RcInit I = *J.rc_init;
+      rc.range = I.range; rc.ffnum = I.ffnum; rc.cache = I.cache; rc.lowc = I.lowc; rc.nbytes = I.nbytes;
+    }
     int m0 = 0, m1 = 0;
     int q = 0;
     for (int bpn = maxbpn; bpn >= 0; bpn--) {
@@ -658,7 +608,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bitplane_decode_kernel(cons
   long long ipos = 0;
   uint32_t range = 0xFFFFFFFFu, code = 0;
   auto getb = [&]() -> uint32_t { const uint32_t b = ipos < in_len ? in[ipos] : 0xffffffffu; ipos++; return b; };
-  for (int i = 0; i < 5; i++) code = (code << 8) + getb();
+  if (J.rc_init) { const RcInit I = *J.rc_init; range = I.range; code = I.code; ipos = I.nbytes; }   // after MapEncoder::Decode
+  else for (int i = 0; i < 5; i++) code = (code << 8) + getb();
 
   for (int bpn = maxbpn; bpn >= 0; bpn--) {
     uint32_t state = 0;

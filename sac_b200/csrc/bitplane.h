@@ -7,6 +7,16 @@
 
 namespace sacb {
 
+// Range-coder state handed from the sparse-PCM map coder (sparse.cu) to the bitplane coder that continues the same
+// payload (EncodeMonoFrame_Mapped / DecodeMonoFrame, libsac.cpp:214-228, 280-298).
+struct RcInit {
+  unsigned long long lowc;   // encoder: low incl. carry
+  long long nbytes;          // encoder: bytes already written to `out`; decoder: bytes already consumed from `in`
+  uint32_t range, ffnum, cache, code;
+  int go;                    // encoder: 0 = the cost ratio did not call for a mapped record; the bitplane job returns at once
+  int pad;
+};
+
 struct BpJob {
   int32_t *buf;          // encode/cost: residuals (signed if signed_input, mapped in place) ; decode: output (signed)
   int n;
@@ -19,6 +29,7 @@ struct BpJob {
   const uint8_t *in;     // decode: payload
   long long in_len;
   uint8_t *msb;          // decode: n bytes scratch
+  const RcInit *rc_init; // null: a fresh coder; else continue from this state (written by an earlier kernel of the stream)
 };
 
 struct BitplaneTables {

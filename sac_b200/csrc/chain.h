@@ -50,6 +50,11 @@ struct ChainDesc {
   int *progress;            // number of decoded samples of this channel
   const int *wait_ctr;      // progress of the other channel (null: no dependency)
   int wait_add;             // need(t) = min(n, max(t + wait_add, 0))  (ch0: -lag; ch1: +nS1)
+  // --- decoder, sparse-PCM channel: err_in holds rank distances among the used sample values (libsac.cpp:157-160,
+  //     map.cpp:188-202); cumulative counts and the sorted used values as built by sparse.cu. null: plain residuals ---
+  const int32_t *unmap_cum;
+  const int32_t *unmap_list;
+  int unmap_mean;           // the prediction is re-based to raw sample values: pi + mean
 };
 
 } // namespace sacb

@@ -583,7 +583,10 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
   // ---- final pass (k=1, whole frame) + payload emission of one frame on a helper engine: it is launched as soon as
   //      the frame's profile is known and runs on its own high-priority stream while the main stream searches the
   //      next frame; results are collected at the end (WriteEncoded order) ----
-  struct Final { Engine *eng = nullptr; bool launched = false; int nchains = 0; std::vector<int> cj, cc; std::vector<size_t> boff; };
+  struct Final {
+    Engine *eng = nullptr; bool launched = false; int nchains = 0; std::vector<int> cj, cc; std::vector<size_t> boff;
+    std::vector<int> sp_of; int nsp = 0; size_t sp_res_off = 0; std::vector<size_t> sp_bytes_off;   // sparse-PCM side (sparse.h)
+  };
   std::vector<Final> fin(nframes);
   const int kHelpers = 4;
   auto collect_final = [&](int f) -> int {
@@ -600,13 +603,22 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
     for (int ch = 0; ch < nch; ch++) {
       int c = -1;
       for (int q = 0; q < F.nchains; q++) if (F.cc[q] == ch) c = q;
-      const long long nb = h->h_sums.p[2 * F.nchains + c];
+      long long nb = h->h_sums.p[2 * F.nchains + c];
       const int maxbpn = h->h_flags.p[F.nchains + c];
+      const uint8_t *src = h->d_bytes.p + F.boff[c];
+      uint16_t flag = (uint16_t)(maxbpn & 0xff);
+      const int k = F.sp_of[c];
+      if (k >= 0 && h->h_sparse.p[k].go && h->h_sparse.p[k].nbytes < nb) {     // size_mapped < size_normal (libsac.cpp:267-275)
+        if (cfg.verbose > 0) std::fprintf(stderr, "  sparse frame %lld -> %lld (%lld)\n", nb, h->h_sparse.p[k].nbytes, h->h_sparse.p[k].nbytes - nb);
+        nb = h->h_sparse.p[k].nbytes;
+        src = h->d_sparse.p + F.sp_bytes_off[k];
+        flag = (uint16_t)((1 << 9) | (h->h_sparse.p[k].maxbpn & 0xff));        // WriteBlockHeader, libsac.cpp:536-541
+      }
       payload.resize((size_t)nb);
-      SACB_CUDA(cudaMemcpyAsync(payload.data(), h->d_bytes.p + F.boff[c], (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
+      SACB_CUDA(cudaMemcpyAsync(payload.data(), src, (size_t)nb, cudaMemcpyDeviceToHost, h->stream));
       SACB_CUDA(cudaStreamSynchronize(h->stream));
       push32(out, (uint32_t)nb); push32(out, (uint32_t)fw[f].mean[ch]); push32(out, (uint32_t)fw[f].mm[2 * ch]); push32(out, (uint32_t)fw[f].mm[2 * ch + 1]);
-      push16(out, (uint16_t)(maxbpn & 0xff));
+      push16(out, flag);
       out.insert(out.end(), payload.begin(), payload.end());
     }
     F.eng = nullptr;
@@ -627,9 +639,16 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
     int rc = h->run_predict(jobs, F.cj, F.cc, stride);
     if (rc) return rc;
     const int nchains = F.nchains = (int)F.cj.size();
-    SACB_CUDA(h->h_bpjobs.reserve(nchains));
-    SACB_CUDA(h->d_bpjobs.reserve(nchains));
-    SACB_CUDA(h->d_csig0.reserve((size_t)65536 * nchains));
+    F.sp_of.assign(nchains, -1); F.nsp = 0;
+    if (cfg.sparse_pcm)
+      for (int c = 0; c < nchains; c++) {
+        const int ch = F.cc[c];
+        const long long lo = (long long)fw[f].mm[2 * ch] + fw[f].mean[ch], hi = (long long)fw[f].mm[2 * ch + 1] + fw[f].mean[ch];
+        if (lo >= -kRemapScale && hi <= kRemapScale) F.sp_of[c] = F.nsp++;
+      }
+    SACB_CUDA(h->h_bpjobs.reserve(nchains + F.nsp));
+    SACB_CUDA(h->d_bpjobs.reserve(nchains + F.nsp));
+    SACB_CUDA(h->d_csig0.reserve((size_t)65536 * (nchains + F.nsp)));
     F.boff.assign(nchains + 1, 0);
     for (int c = 0; c < nchains; c++) F.boff[c + 1] = F.boff[c] + (((size_t)fw[f].n * 4 + 1024 + 15) & ~size_t(15));
     SACB_CUDA(h->d_bytes.reserve(F.boff[nchains]));
@@ -640,9 +659,53 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
       b.csig0 = h->d_csig0.p + (size_t)65536 * c; b.out = h->d_bytes.p + F.boff[c];
       b.nbytes = h->d_sums.p + 2 * (size_t)nchains + c; b.maxbpn_out = h->d_flags.p + nchains + c;
     }
-    SACB_CUDA(cudaMemcpyAsync(h->d_bpjobs.p, h->h_bpjobs.p, sizeof(BpJob) * nchains, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(launch_bitplane(h->bt, h->d_bpjobs.p, nchains, 1, h->stream));
+    // ---- sparse-PCM (FrameCoder::EncodeMonoFrame, libsac.cpp:253-278): the channel is ALSO coded as rank distances
+    //      among the sample values that occur, behind the coded map of those values, when the L1 ratio calls for it;
+    //      the shorter record is kept at collection. The reference's map covers |value| <= 32768 only and its mapped
+    //      records of wider samples do not decode (map.cpp:126-166): such channels stay unmapped here. ----
+    int njobs_bp = nchains;
+    if (F.nsp > 0) {
+      SparseJobs SJ;
+      std::memset(&SJ, 0, sizeof(SJ));
+      SJ.n = F.nsp;
+      const size_t nsp = (size_t)F.nsp;
+      const size_t o_rc = 0, o_res = o_rc + sizeof(RcInit) * nsp, o_used = (o_res + sizeof(SparseOut) * nsp + 127) & ~size_t(127);
+      const size_t o_cum = o_used + kRemapUsedBytes * nsp, cumb = ((size_t)kRemapDom * 4 + 127) & ~size_t(127);
+      const size_t o_list = o_cum + cumb * nsp, o_em = o_list + cumb * nsp, emb = stride * 4;
+      const size_t o_bytes = o_em + emb * nsp, bytesb = ((size_t)fw[f].n * 4 + 1024 + kMapBytesMax + 127) & ~size_t(127);
+      SACB_CUDA(h->d_sparse.reserve(o_bytes + bytesb * nsp));
+      SACB_CUDA(cudaMemsetAsync(h->d_sparse.p, 0, o_cum, h->stream));
+      F.sp_res_off = o_res; F.sp_bytes_off.assign(nsp, 0);
+      for (int c = 0; c < nchains; c++) {
+        const int k = F.sp_of[c];
+        if (k < 0) continue;
+        const int ch = F.cc[c];
+        SparseJob &j = SJ.j[k];
+        j.s = fw[f].win->d_planes[ch]; j.e = h->d_resid.p + (size_t)c * stride; j.n = fw[f].n; j.mean = fw[f].mean[ch];
+        j.em = reinterpret_cast<int32_t *>(h->d_sparse.p + o_em + emb * k);
+        j.used = h->d_sparse.p + o_used + kRemapUsedBytes * k;
+        j.cum = reinterpret_cast<int32_t *>(h->d_sparse.p + o_cum + cumb * k);
+        j.ulist = reinterpret_cast<int32_t *>(h->d_sparse.p + o_list + cumb * k);
+        j.bytes = h->d_sparse.p + o_bytes + bytesb * k; F.sp_bytes_off[k] = o_bytes + bytesb * k;
+        j.rc = reinterpret_cast<RcInit *>(h->d_sparse.p + o_rc) + k;
+        j.res = reinterpret_cast<SparseOut *>(h->d_sparse.p + o_res) + k;
+        BpJob &b = h->h_bpjobs.p[nchains + k];
+        std::memset(&b, 0, sizeof(b));
+        b.buf = j.em; b.n = fw[f].n; b.signed_input = 1; b.maxbpn = -1;
+        b.csig0 = h->d_csig0.p + (size_t)65536 * (nchains + k); b.out = j.bytes;
+        b.nbytes = &j.res->nbytes; b.maxbpn_out = &j.res->maxbpn; b.rc_init = j.rc;
+      }
+      SACB_CUDA(launch_sparse_encode(h->bt, SJ, h->stream));
+      h->launches += 4; h->last_launches[2] += 4;
+      njobs_bp = nchains + F.nsp;
+    }
+    SACB_CUDA(cudaMemcpyAsync(h->d_bpjobs.p, h->h_bpjobs.p, sizeof(BpJob) * njobs_bp, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(launch_bitplane(h->bt, h->d_bpjobs.p, njobs_bp, 1, h->stream));
     h->launches++; h->last_launches[1]++;
+    if (F.nsp > 0) {
+      SACB_CUDA(h->h_sparse.reserve((size_t)F.nsp));
+      SACB_CUDA(cudaMemcpyAsync(h->h_sparse.p, h->d_sparse.p + F.sp_res_off, sizeof(SparseOut) * F.nsp, cudaMemcpyDeviceToHost, h->stream));
+    }
     SACB_CUDA(h->h_sums.reserve((size_t)3 * nchains));
     SACB_CUDA(h->h_flags.reserve((size_t)2 * nchains));
     SACB_CUDA(cudaMemcpyAsync(h->h_sums.p, h->d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, h->stream));
@@ -740,13 +803,14 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
   long long pos = hdr;
   int32_t mean[2] = {0, 0}, mm[4] = {0, 0, 0, 0};
   int maxbpn[2] = {0, 0};
+  bool mapped[2] = {false, false};
   long long poff[2] = {0, 0}, plen[2] = {0, 0};
   for (int ch = 0; ch < nch; ch++) {
     if (pos + 18 > len) { set_error("truncated block header"); return SAC_E_FORMAT; }
     plen[ch] = get32(in + pos);
     mean[ch] = (int32_t)get32(in + pos + 4); mm[2 * ch] = (int32_t)get32(in + pos + 8); mm[2 * ch + 1] = (int32_t)get32(in + pos + 12);
     const uint16_t flag = get16(in + pos + 16);
-    if (flag >> 9) { set_error("sparse-pcm mapped frames are not supported"); return SAC_E_UNSUPPORTED; }
+    mapped[ch] = (flag >> 9) != 0;                                  // ReadBlockHeader, libsac.cpp:551-564
     maxbpn[ch] = flag & 0xff;
     pos += 18;
     poff[ch] = pos;
@@ -777,6 +841,32 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
     b.msb = e->d_bytes.p + bo;
     bo += stride;
   }
+  // ---- sparse-PCM channels: the payload opens with the coded map of the used sample values (DecodeMonoFrame,
+  //      libsac.cpp:280-298); the bitplane decoder continues the same range decoder ----
+  SparseJobs SJ;
+  std::memset(&SJ, 0, sizeof(SJ));
+  int sp_of[2] = {-1, -1};
+  for (int ch = 0; ch < nch; ch++) if (mapped[ch]) sp_of[ch] = SJ.n++;
+  if (SJ.n > 0) {
+    const size_t nsp = (size_t)SJ.n, o_used = (sizeof(RcInit) * nsp + 127) & ~size_t(127), o_cum = o_used + kRemapUsedBytes * nsp;
+    const size_t cumb = ((size_t)kRemapDom * 4 + 127) & ~size_t(127), o_list = o_cum + cumb * nsp;
+    SACB_CUDA(e->d_sparse.reserve(o_list + cumb * nsp));
+    SACB_CUDA(cudaMemsetAsync(e->d_sparse.p, 0, o_cum, e->stream));
+    for (int ch = 0; ch < nch; ch++) {
+      const int k = sp_of[ch];
+      if (k < 0) continue;
+      SparseJob &j = SJ.j[k];
+      j.n = n; j.mean = mean[ch];
+      j.used = e->d_sparse.p + o_used + kRemapUsedBytes * k;
+      j.cum = reinterpret_cast<int32_t *>(e->d_sparse.p + o_cum + cumb * k);
+      j.ulist = reinterpret_cast<int32_t *>(e->d_sparse.p + o_list + cumb * k);
+      j.bytes = const_cast<uint8_t *>(e->h_bpjobs.p[ch].in); j.in_len = plen[ch];
+      j.rc = reinterpret_cast<RcInit *>(e->d_sparse.p) + k;
+      e->h_bpjobs.p[ch].rc_init = j.rc;
+    }
+    SACB_CUDA(launch_sparse_decode(e->bt, SJ, e->stream));
+    e->launches += 2; e->last_launches[2] += 2;
+  }
   SACB_CUDA(cudaMemcpyAsync(e->d_bpjobs.p, e->h_bpjobs.p, sizeof(BpJob) * nch, cudaMemcpyHostToDevice, e->stream));
   SACB_CUDA(cudaEventRecord(e->ev[2], e->stream));
   SACB_CUDA(launch_bitplane(e->bt, e->d_bpjobs.p, nch, 2, e->stream));
@@ -799,6 +889,9 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
     const int actual = fill_chain(d, hp, nch, cc, 1, cpl, 0, n, mm);
     d.own_out = dplanes[actual];
     d.err_in = e->d_resid.p + (size_t)actual * stride;
+    if (sp_of[actual] >= 0) {                                      // UnpredictFrame, libsac.cpp:157-160
+      d.unmap_cum = SJ.j[sp_of[actual]].cum; d.unmap_list = SJ.j[sp_of[actual]].ulist; d.unmap_mean = mean[actual];
+    }
     d.resid = nullptr;
     d.scratch = e->d_scratch.p + soff[cc]; d.scratch_doubles = soff[cc + 1] - soff[cc];
     d.l1sum = nullptr; d.sqsum = nullptr; d.flags = e->d_flags.p + cc;

@@ -187,7 +187,7 @@ void Engine::destroy()
   if (stream) cudaStreamSynchronize(stream);
   d_descs.release(); h_descs.release(); d_scratch.release(); d_scratch_ols.release(); d_plpc.release(); d_resid.release(); d_sums.release(); d_flags.release();
   h_sums.release(); h_flags.release(); d_bpjobs.release(); h_bpjobs.release(); d_csig0.release(); d_hist.release();
-  d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release();
+  d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release(); d_sparse.release(); h_sparse.release();
   if (!is_helper) bt.destroy();
   for (auto &e : ev) if (e) cudaEventDestroy(e);
   if (ev_wait) cudaEventDestroy(ev_wait);

@@ -3,6 +3,7 @@
 #define SAC_B200_ENGINE_H
 #include "bitplane.h"
 #include "chain.h"
+#include "sparse.h"
 #include "sac_b200.h"
 #include <cuda_runtime.h>
 #include <string>
@@ -95,6 +96,8 @@ struct Engine {           // sac_engine
   PinBuf<double> h_cost;
   DevBuf<uint8_t> d_bytes;        // payload / msb scratch
   PinBuf<int32_t> h_stage;        // pinned staging for sample uploads
+  DevBuf<uint8_t> d_sparse;       // sparse-PCM side of a final pass / a decode: coder hand-over, used map, counts, mapped residuals, payload
+  PinBuf<SparseOut> h_sparse;
 
   // helper engines: own stream (high priority) and pools on the same device, used for the final pass of a frame
   // while the main stream already searches the next frame; they share this engine's model tables

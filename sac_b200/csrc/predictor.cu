@@ -123,6 +123,19 @@ template <bool DECODE> __device__ __forceinline__ int32_t load_sample(const int3
 // packed lower-triangular index, row-major, rows 0..n (row n holds b)
 __device__ __forceinline__ int tri(int i, int c) { return ((i * (i + 1)) >> 1) + c; }
 
+// Remap::Unmap (map.cpp:188-202) in O(1): the |m|-th used sample value above (m > 0) or below (m < 0) the re-based
+// prediction, from the cumulative counts C(v) = #{used u <= v} and the ascending list U of the used values (sparse.cu)
+__device__ __forceinline__ int32_t unmap_residual(const ChainDesc &d, int32_t pi, int32_t m)
+{
+  if (m == 0) return 0;
+  const int pred = pi + d.unmap_mean;
+  const int nused = __ldg(d.unmap_cum + 65536);
+  auto C = [&](int v) { return v < -32768 ? 0 : __ldg(d.unmap_cum + min(v, 32768) + 32768); };
+  int idx = m > 0 ? C(pred) + m - 1 : C(pred - 1) + m;
+  idx = min(max(idx, 0), nused - 1);          // a damaged stream can ask for a rank that does not exist (the reference would not return)
+  return __ldg(d.unmap_list + idx) - pred;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 template <bool DECODE>
 __global__ void __launch_bounds__(kBlockThreads, 3) predictor_kernel(const ChainDesc *__restrict__ descs)
@@ -342,6 +355,7 @@ __global__ void __launch_bounds__(kBlockThreads, 3) predictor_kernel(const Chain
     int32_t vali, e;
     if (DECODE) {
       e = d.err_in[t];
+      if (d.unmap_cum) e = unmap_residual(d, pi, e);
       vali = pi + e;
       if (lane == 0) d.own_out[t] = vali;
     } else {

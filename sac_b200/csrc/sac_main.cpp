@@ -33,7 +33,7 @@ static const char kHelp[] =
     "   --zero-mean        zero-mean input\n"
     "   --adapt-block      accepted (adaptive splitting not implemented)\n"
     "   --framelen=n       def=20 seconds\n"
-    "   --sparse-pcm       accepted (pcm modelling not implemented)\n"
+    "   --sparse-pcm       enable pcm modelling (default), --sparse-pcm=no disables it\n"
     "  B200 options\n"
     "   --gpu=n            CUDA device (def=0)\n"
     "   --frame-parallel[=1|2]  search all frames of the file concurrently (implies --opt-reset semantics):\n"
