@@ -337,7 +337,7 @@ def main():
             "e2e": {"value": e2e, "unit": "MSamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(l_timed),
             "chains": {"requested": dd_timed[0], "evaluated": dd_timed[1], "ols_stages_evaluated": dd_timed[2],
-                       "note": "exact de-duplication: chains / OLS stages of a generation with identical inputs run once (DESIGN.md section 4.5)"},
+                       "note": "exact de-duplication: chains / OLS stages of a generation with identical inputs run once (DESIGN.md section 4.6)"},
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "note": "the path is a set of serial fp64/integer recurrences bound by instruction latency, not by HBM: "
