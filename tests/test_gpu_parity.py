@@ -280,7 +280,8 @@ def test_frame_encode_with_de_search_roundtrips(engine):
     cfg = sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=36, sigma=0.2, cost_kind=sb.COST_BITPLANE, max_framelen=1, search=sb.SEARCH_DE)
     l0 = engine.launches
     rec, prof = engine.frames_encode(cfg, [raw], 44100)
-    assert engine.launches - l0 == 3 * 3 + 3           # 3 population evaluations + the final pass, 3 kernels each
+    # 3 population evaluations + the final pass, 3 kernels each; the final pass also runs the 4 sparse-PCM kernels (sparse.cu)
+    assert engine.launches - l0 == 3 * 3 + 3 + 4
     dec, used = engine.frame_decode(2, rec, 44100)
     assert used == len(rec) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1])
     assert len(rec) <= len(base)
