@@ -99,11 +99,14 @@ def test_cli_listing_of_a_reference_file_matches_the_reference_cli():
     gold = os.path.join(ROOT, "tests", "golden")
     cli = os.path.join(ROOT, "sac_b200", "sac")
     assert os.path.exists(cli), "build the CLI first (make -C sac_b200/csrc)"
-    for flag, ext in (("--listfull", "listfull"), ("--list", "list")):
-        out = subprocess.run([cli, flag, "ref_stereo_quarter_normal.sac"], cwd=gold, capture_output=True, text=True, timeout=60).stdout
+    # second file: a frame the reference coded rank-mapped (sparse PCM): block flag 1<<9 | maxbpn_map
+    for stem, flag, ext in (("ref_stereo_quarter_normal", "--listfull", "listfull"), ("ref_stereo_quarter_normal", "--list", "list"),
+                            ("ref_mono_sparse_normal", "--listfull", "listfull")):
+        out = subprocess.run([cli, flag, stem + ".sac"], cwd=gold, capture_output=True, text=True, timeout=60).stdout
         got = out[out.index("Open:"):].splitlines()
-        want = open(os.path.join(gold, "ref_stereo_quarter_normal.%s.txt" % ext)).read().splitlines()
+        want = open(os.path.join(gold, "%s.%s.txt" % (stem, ext))).read().splitlines()
         assert got == want, (flag, got, want)
+    assert "sparse_pcm: 1" in open(os.path.join(gold, "ref_mono_sparse_normal.listfull.txt")).read()
 
 
 def test_de_and_cma_drivers_match_reference_goldens():
