@@ -1,4 +1,5 @@
-"""world_size-2 run of the multi-GPU plumbing on CPU (gloo): unit sharding and the final bitstream gather."""
+"""world_size-2 runs of the multi-GPU plumbing on CPU (gloo): unit sharding + final bitstream gather, and the
+candidate-sharded generation (one all_gather of costs per generation, searches in lockstep)."""
 import os
 import sys
 
@@ -40,3 +41,59 @@ def test_two_rank_gather():
     assert r0[1] == [100, 201, 300, 401, 500] and r0[2] == [1, 2, 3, 4, 5]
     assert r1[1] is None
     assert r0[3] == 2.0 and r1[3] == 2.0
+
+
+def _objective(X, xmin, xmax):
+    import numpy as np
+    z = (X - xmin) / (xmax - xmin)
+    return np.sum((z - 0.37) ** 2, axis=1) + 0.05 * np.sum(np.cos(9 * z), axis=1)
+
+
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch.distributed as dist
+    import sac_b200 as sb
+    from sac_b200 import shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    vmin, vmax, vdef = sb.base_profile()
+    idx = list(sb.SEARCH_DIMS)
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    seen = []
+
+    def eval_rows(Xs):
+        seen.append(len(Xs))
+        return _objective(Xs, xmin, xmax)
+
+    out = []
+    for nfunc, pop in ((61, 7), (40, 16)):          # odd generation sizes: ragged slices, padded collective
+        best, xb = shard.sharded_dds(eval_rows, xmin, xmax, xs, nfunc, pop, 0.25, rank, world)
+        out.append((float(best), xb.tobytes()))
+    q.put((rank, out, sum(seen)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_candidate_sharded_search_is_the_single_rank_search():
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import sac_b200 as sb
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)])
+    for p in procs: p.join(60)
+    vmin, vmax, vdef = sb.base_profile()
+    idx = list(sb.SEARCH_DIMS)
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    total = 0
+    for k, (nfunc, pop) in enumerate(((61, 7), (40, 16))):
+        n_eval = []
+        best, xb = sb.dds_run(lambda X: (n_eval.append(len(X)), _objective(X, xmin, xmax))[1], xmin, xmax, xs, nfunc, pop, 0.25)
+        total += sum(n_eval)
+        for r in range(2):
+            assert res[r][1][k] == (float(best), xb.tobytes())       # every rank ends with the single-rank result, bit for bit
+    assert res[0][2] + res[1][2] == total and abs(res[0][2] - res[1][2]) <= 12   # the work was split, nothing evaluated twice
