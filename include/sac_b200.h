@@ -159,6 +159,12 @@ long long sac_frame_decode(sac_engine *, int nch, const uint8_t *in, long long l
 typedef struct sac_file_stats { long long in_bytes, out_bytes; int numsamples, nch, samplerate, bits, nframes; double seconds; uint8_t md5[16]; int md5_ok; } sac_file_stats;
 int sac_encode_file(sac_engine *, const sac_cfg *, const char *wav_path, const char *sac_path, sac_file_stats *);
 int sac_decode_file(sac_engine *, const char *sac_path, const char *wav_path, sac_file_stats *);
+/* Host part of Codec::EncodeFile alone (libsac.cpp:782-835; wav.cpp:167-263, sac.cpp:15-38; NO GPU needed): parses the
+ * WAV image and writes what precedes the first frame record of the .sac file -- header, metadata (all WAV chunks), MD5 of
+ * the PCM bytes -- to out[0,*out_len); frame_lengths[0,st->nframes) receives the samples per frame record (reads of
+ * max_framelen seconds, split by Codec::Analyse when cfg->adapt_block). sac_encode_memory = this + sac_frames_encode. */
+int sac_container_plan(const sac_cfg *, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap, long long *out_len,
+                       int *frame_lengths, int cap_frames, sac_file_stats *);
 /* in-memory variants (host buffers) used by bench.py's e2e leg */
 int sac_encode_memory(sac_engine *, const sac_cfg *, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap,
                       long long *out_len, sac_file_stats *);

@@ -188,6 +188,19 @@ def cma_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.0):
     return de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init, entry="sac_cma_run")
 
 
+def container_plan(cfg, wav_bytes, cap_frames=4096):
+    """host-only: (.sac bytes preceding the first frame record, [samples per frame record], FileStats)"""
+    wav = np.frombuffer(wav_bytes, np.uint8)
+    cap = len(wav) + 65536
+    out = np.zeros(cap, np.uint8)
+    olen = C.c_longlong(0)
+    fl = np.zeros(cap_frames, np.int32)
+    st = FileStats()
+    _chk(lib().sac_container_plan(C.byref(cfg), _p(wav, _u8p), len(wav), _p(out, _u8p), cap, C.byref(olen), _p(fl, _i32p), cap_frames,
+                                  C.byref(st)), "sac_container_plan")
+    return out[:olen.value].tobytes(), fl[:st.nframes].tolist(), st
+
+
 class Window:
     """a (sub)frame resident in HBM: mean-free planes + stats (what FrameCoder::Optimize's cost lambda captures)"""
 

@@ -987,35 +987,43 @@ std::vector<SubFrame> analyse_subframes(const std::vector<std::vector<int32_t>> 
 // =====================================================================================================================
 // files
 // =====================================================================================================================
-static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out, sac_file_stats *st)
-{
-  const auto t0 = std::chrono::steady_clock::now();
+// Everything of Codec::EncodeFile that happens on the host before the first frame is coded (libsac.cpp:782-835): WAV
+// header parse, .sac header + metadata + MD5 of the PCM bytes, reads of max_framesize samples split into sub-frames.
+struct ContainerPlan {
   WavInfo wi;
+  size_t md5pos = 0;
+  uint8_t md5[16];
+  int max_framesize = 0;
+  std::vector<std::vector<int32_t>> store;                           // frame f, channel ch at store[f * nch + ch]
+  std::vector<int> ns;                                               // samples per frame
+};
+static int container_plan(const sac_cfg &cfg, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out, ContainerPlan &cp, bool keep_samples)
+{
+  WavInfo &wi = cp.wi;
   int rc = wav_parse(wav, wav_len, wi);
   if (rc) return rc;
   if (!(wi.bits <= 24 && (wi.nch == 1 || wi.nch == 2)) || wi.blockalign <= 0 || wi.blockalign % wi.nch) {
     set_error("unsupported input format: must be 1-16 bit, mono/stereo, pcm");          // cmdline.cpp:253-262
     return SAC_E_UNSUPPORTED;
   }
-  const int max_framesize = cfg.max_framelen * wi.samplerate;
+  const int max_framesize = cp.max_framesize = cfg.max_framelen * wi.samplerate;
   if (max_framesize <= 0) { set_error("bad frame length"); return SAC_E_ARG; }
-  // ---- .sac header (sac.cpp:15-38) + MD5 placeholder ----
+  // ---- .sac header (sac.cpp:15-38) + MD5 ----
   out.clear();
   out.push_back('S'); out.push_back('A'); out.push_back('C'); out.push_back('2');
   push16(out, (uint16_t)wi.nch); push32(out, (uint32_t)wi.samplerate); push16(out, (uint16_t)wi.bits); push32(out, wi.numsamples);
   out.push_back((uint8_t)cfg.max_framelen); out.push_back(0);
   push32(out, wi.metadatasize());
   pack_metadata(wi, out);
-  const size_t md5pos = out.size();
-  out.resize(out.size() + 16, 0);
-  // ---- samples ----
+  cp.md5pos = out.size();
   const uint8_t *pcm = wav + wi.data_pos;
   const size_t pcm_bytes = (size_t)wi.numsamples * wi.blockalign;
   Md5 md5;
   md5.update(pcm, pcm_bytes);
-  // reads of max_framesize samples, each split into sub-frames (Codec::EncodeFile, libsac.cpp:805-835)
-  std::vector<std::vector<int32_t>> store;
-  std::vector<int> ns;
+  md5.final(cp.md5);
+  out.insert(out.end(), cp.md5, cp.md5 + 16);
+  // ---- reads of max_framesize samples, each split into sub-frames (Codec::EncodeFile, libsac.cpp:805-835) ----
+  cp.store.clear(); cp.ns.clear();
   for (uint32_t first = 0; first < wi.numsamples; first += (uint32_t)max_framesize) {
     const int nread = (int)std::min<uint32_t>((uint32_t)max_framesize, wi.numsamples - first);
     std::vector<std::vector<int32_t>> pl(wi.nch, std::vector<int32_t>(nread));
@@ -1025,26 +1033,34 @@ static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_
     else { SubFrame s; s.state = 0; s.start = 0; s.length = nread; sub.push_back(s); }
     for (const SubFrame &s : sub) {
       if (s.length <= 0) continue;
-      for (int ch = 0; ch < wi.nch; ch++) store.emplace_back(pl[ch].begin() + s.start, pl[ch].begin() + s.start + s.length);
-      ns.push_back(s.length);
+      if (keep_samples)
+        for (int ch = 0; ch < wi.nch; ch++) cp.store.emplace_back(pl[ch].begin() + s.start, pl[ch].begin() + s.start + s.length);
+      cp.ns.push_back(s.length);
     }
   }
-  const int nframes = (int)ns.size();
+  return SAC_OK;
+}
+
+static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out, sac_file_stats *st)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  ContainerPlan cp;
+  int rc = container_plan(cfg, wav, wav_len, out, cp, true);
+  if (rc) return rc;
+  const WavInfo &wi = cp.wi;
+  const int nframes = (int)cp.ns.size();
   std::vector<const int32_t *> ptrs((size_t)nframes * wi.nch);
-  for (size_t i = 0; i < ptrs.size(); i++) ptrs[i] = store[i].data();
+  for (size_t i = 0; i < ptrs.size(); i++) ptrs[i] = cp.store[i].data();
   float prof[kProfileSize];
   for (int i = 0; i < kProfileSize; i++) prof[i] = kBaseProfile[i][2];
   if (nframes > 0) {
-    rc = frames_encode(e, cfg, wi.nch, max_framesize, nframes, ptrs.data(), ns.data(), prof, out);
+    rc = frames_encode(e, cfg, wi.nch, cp.max_framesize, nframes, ptrs.data(), cp.ns.data(), prof, out);
     if (rc) return rc;
   }
-  uint8_t dig[16];
-  md5.final(dig);
-  std::memcpy(out.data() + md5pos, dig, 16);
   if (st) {
     std::memset(st, 0, sizeof(*st));
     st->in_bytes = (long long)wav_len; st->out_bytes = (long long)out.size(); st->numsamples = (int)wi.numsamples; st->nch = wi.nch;
-    st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, dig, 16); st->md5_ok = 1;
+    st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, cp.md5, 16); st->md5_ok = 1;
     st->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
   return SAC_OK;
@@ -1326,6 +1342,26 @@ long long sac_frame_decode(sac_engine *h, int nch, const uint8_t *in, long long 
   for (int ch = 0; ch < nch; ch++) std::memcpy(planes_out[ch], planes[ch].data(), sizeof(int32_t) * (size_t)n);
   *numsamples = n;
   return used;
+}
+
+int sac_container_plan(const sac_cfg *cfg, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap, long long *out_len,
+                       int *frame_lengths, int cap_frames, sac_file_stats *st)
+{
+  if (!cfg || !wav || wav_len <= 0) { set_error("null argument"); return SAC_E_ARG; }
+  std::vector<uint8_t> o;
+  ContainerPlan cp;
+  int rc = container_plan(*cfg, wav, (size_t)wav_len, o, cp, false);
+  if (rc) return rc;
+  if (out_len) *out_len = (long long)o.size();
+  if (out) { if ((long long)o.size() > cap) { set_error("output buffer too small"); return SAC_E_ARG; } std::memcpy(out, o.data(), o.size()); }
+  const int nframes = (int)cp.ns.size();
+  if (frame_lengths) { if (nframes > cap_frames) { set_error("frame_lengths too small"); return SAC_E_ARG; } std::copy(cp.ns.begin(), cp.ns.end(), frame_lengths); }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->in_bytes = wav_len; st->out_bytes = (long long)o.size(); st->numsamples = (int)cp.wi.numsamples; st->nch = cp.wi.nch;
+    st->samplerate = cp.wi.samplerate; st->bits = cp.wi.bits; st->nframes = nframes; std::memcpy(st->md5, cp.md5, 16); st->md5_ok = 1;
+  }
+  return SAC_OK;
 }
 
 int sac_encode_memory(sac_engine *h, const sac_cfg *cfg, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap,

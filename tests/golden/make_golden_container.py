@@ -1,0 +1,95 @@
+"""Generates tests/golden/golden_container.json with the UNMODIFIED reference CLI (oracle/_ref/sac): for WAV images of the
+shapes src/file/wav.cpp handles (8/16/24-bit, fmt chunk sizes 16/18/40 incl. WAVE_FORMAT_EXTENSIBLE, extra chunks before
+and after 'data', odd-sized chunks, a truncated data chunk, several frames) it records the bytes of the .sac file that
+precede the first frame record (header, metadata, MD5) and the samples of every frame record. The WAVs are rebuilt
+deterministically by wav_case(); nothing but the JSON is committed. Run in the build container only:
+
+    make -C oracle ref && python tests/golden/make_golden_container.py
+"""
+import hashlib
+import json
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from synth_wav import synth_pcm  # noqa: E402
+
+
+def _chunk(cid, payload, pad=True):
+    b = cid + struct.pack("<I", len(payload)) + payload
+    return b + (b"\0" if pad and len(payload) & 1 else b"")
+
+
+def wav_case(name):
+    """-> WAV image (bytes). 16-bit-range synthetic audio re-quantised to the container's width."""
+    spec = CASES[name]
+    sr, nch, width, secs = spec["sr"], spec["nch"], spec["width"], spec["secs"]
+    x = synth_pcm(secs, nch, spec["seed"], sr).astype(np.int32)
+    if width == 1:
+        data = ((x >> 8) + 128).astype(np.uint8).tobytes()
+    elif width == 2:
+        data = x.astype("<i2").tobytes()
+    else:
+        v = (x << 8) + (np.arange(x.size).reshape(x.shape) % 251)
+        b = v.astype("<i4").tobytes()
+        data = b"".join(b[i:i + 3] for i in range(0, len(b), 4))
+    bits = spec.get("bits", 8 * width)
+    fmt = struct.pack("<HHIIHH", 0xFFFE if spec["fmt"] == 40 else 1, nch, sr, sr * nch * width, nch * width, 8 * width)
+    if spec["fmt"] == 18:
+        fmt += struct.pack("<H", 0)
+    elif spec["fmt"] == 40:
+        fmt += struct.pack("<HHI", 22, bits, 3 if nch == 2 else 4) + struct.pack("<H", 1) + bytes.fromhex("000000001000800000aa00389b71")
+    body = b"WAVE" + _chunk(b"fmt ", fmt)
+    for cid, payload in spec.get("before", []):
+        body += _chunk(cid.encode(), payload.encode())
+    declared = len(data) + spec.get("declare_extra", 0)
+    body += b"data" + struct.pack("<I", declared) + data
+    if declared & 1 and not spec.get("declare_extra"):
+        body += b"\0"
+    for cid, payload in spec.get("after", []):
+        body += _chunk(cid.encode(), payload.encode())
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+CASES = {
+    "pcm16_stereo": dict(sr=44100, nch=2, width=2, secs=0.3, seed=71, fmt=16),
+    "pcm8_mono": dict(sr=22050, nch=1, width=1, secs=0.4, seed=72, fmt=16),
+    "pcm24_stereo_extensible": dict(sr=48000, nch=2, width=3, secs=0.2, seed=73, fmt=40, bits=24),
+    "pcm16_mono_fmt18": dict(sr=44100, nch=1, width=2, secs=0.25, seed=74, fmt=18),
+    "chunks_before_and_after": dict(sr=32000, nch=2, width=2, secs=0.25, seed=75, fmt=16, before=[("LIST", "INFOabc"), ("fact", "1234")],
+                                    after=[("id3 ", "tag-bytes-odd"), ("bext", "even")]),
+    "truncated_data": dict(sr=44100, nch=2, width=2, secs=0.2, seed=76, fmt=16, declare_extra=4000),
+    "three_frames_8k": dict(sr=8000, nch=1, width=2, secs=45.0, seed=77, fmt=16),
+}
+
+
+def main():
+    sac = os.path.join(ROOT, "oracle", "_ref", "sac")
+    assert os.path.exists(sac), "build oracle/_ref first (make -C oracle ref)"
+    out = {"generator": "tests/golden/make_golden_container.py", "cases": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in CASES:
+            wav = wav_case(name)
+            open(os.path.join(tmp, "a.wav"), "wb").write(wav)
+            r = subprocess.run([sac, "--encode", "--normal", "a.wav", "a.sac"], cwd=tmp, capture_output=True, text=True)
+            assert r.returncode == 0, (name, r.stdout, r.stderr)
+            img = open(os.path.join(tmp, "a.sac"), "rb").read()
+            mds = struct.unpack("<I", img[18:22])[0]
+            prefix = img[:22 + mds + 16]
+            lst = subprocess.run([sac, "--listfull", "a.sac"], cwd=tmp, capture_output=True, text=True).stdout
+            frames = [int(l.split()[2]) for l in lst.splitlines() if l.startswith("Frame ")]
+            out["cases"].append(dict(name=name, wav_sha1=hashlib.sha1(wav).hexdigest(), prefix_len=len(prefix), prefix_hex=prefix.hex(),
+                                     frames=frames))
+            print(name, len(wav), "->", len(img), "prefix", len(prefix), "frames", frames)
+    json.dump(out, open(os.path.join(HERE, "golden_container.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

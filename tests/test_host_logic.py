@@ -161,3 +161,29 @@ def test_adaptive_subframe_split_matches_the_reference_cli():
             assert sum(l for _, l, _ in sub) == len(blk) and all(s == sum(x[1] for x in sub[:i]) for i, (s, _, _) in enumerate(sub))
             frames += [l for _, l, _ in sub]
         assert frames == c["frames"], (c["name"], frames, c["frames"])
+
+
+def test_container_prefix_and_frame_plan_match_the_reference_cli():
+    """WAV parsing + .sac container, host only: for WAV images of every shape src/file/wav.cpp handles
+    (8/16/24-bit, fmt sizes 16/18/40 incl. WAVE_FORMAT_EXTENSIBLE, chunks before/after 'data', odd chunk sizes, a truncated
+    data chunk, several frames) sac_container_plan writes exactly the bytes the UNMODIFIED reference CLI wrote ahead of the
+    first frame record (header, metadata, MD5 of the PCM bytes) and plans the same frame records
+    (tests/golden/make_golden_container.py)."""
+    import hashlib, json, sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_container import wav_case
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_container.json")))
+    assert len(g["cases"]) >= 7
+    for c in g["cases"]:
+        wav = wav_case(c["name"])
+        assert hashlib.sha1(wav).hexdigest() == c["wav_sha1"], c["name"]
+        prefix, frames, st = sb.container_plan(sb.make_cfg("normal"), wav)
+        assert prefix.hex() == c["prefix_hex"], c["name"]
+        assert frames == c["frames"] and st.nframes == len(frames) and st.numsamples == sum(frames), c["name"]
+    # inputs the reference CLI refuses (cmdline.cpp:253-262, wav.cpp:196-203) are refused with an error, not coded
+    bad = bytearray(wav_case("pcm16_stereo")); bad[20] = 3                       # WAVE_FORMAT_IEEE_FLOAT
+    with pytest.raises(sb.SacError):
+        sb.container_plan(sb.make_cfg("normal"), bytes(bad))
+    with pytest.raises(sb.SacError):
+        sb.container_plan(sb.make_cfg("normal"), b"RIFF\x04\x00\x00\x00WAVX")
