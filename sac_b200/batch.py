@@ -1,0 +1,122 @@
+"""Batch of files across the GPUs of one box (BASELINE.json configs[3], SURVEY.md section 8e "files: always independent"):
+one process per GPU (torchrun), files dealt to ranks by size (longest first onto the least loaded rank), each rank
+encodes its files on its own GPU with no data-path collective, the .sac images travel to rank 0 in ONE gather at the end
+(sac_b200/shard.py) and rank 0 writes them. The reference's equivalent is one `sac --encode` process per file.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \\
+        -m sac_b200.batch --best --opt-cfg=dds,128 --out outdir a.wav b.wav ...
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+
+def assign_files(sizes, world):
+    """longest-processing-time-first: -> list (per rank) of file indices. Deterministic on every rank."""
+    order = sorted(range(len(sizes)), key=lambda i: (-sizes[i], i))
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append(i); load[r] += sizes[i]
+    return [sorted(x) for x in out]
+
+
+def encode_batch(paths, out_dir, encode_fn, rank=0, world=1, device=None):
+    """encode_fn(wav_bytes) -> sac_bytes (this rank's GPU). Every rank must call this with the same `paths`.
+    Returns on rank 0: [(path, in_bytes, out_bytes)] in input order, and the seconds of the slowest rank (device-timed by
+    the caller's encode_fn; here: wall around this rank's files, max over ranks)."""
+    from . import shard
+    sizes = [os.path.getsize(p) for p in paths]
+    mine = assign_files(sizes, world)[rank]
+    t0 = time.perf_counter()
+    local = {}
+    for i in mine:
+        with open(paths[i], "rb") as f:
+            local[i] = encode_fn(f.read())
+    secs = shard.max_over_ranks(time.perf_counter() - t0, device)
+    got = _gather(local, len(paths), mine, rank, world, device)
+    if rank != 0:
+        return None, secs
+    os.makedirs(out_dir, exist_ok=True)
+    rep = []
+    for i, p in enumerate(paths):
+        dst = os.path.join(out_dir, os.path.splitext(os.path.basename(p))[0] + ".sac")
+        with open(dst, "wb") as f:
+            f.write(got[i])
+        rep.append((p, sizes[i], len(got[i])))
+    return rep, secs
+
+
+def _gather(local, n_units, mine, rank, world, device):
+    """shard.gather_bitstreams assumes round-robin ownership; files are dealt by size, so ownership travels first"""
+    from . import shard
+    if world == 1:
+        return [local[i] for i in range(n_units)]
+    import torch
+    import torch.distributed as dist
+    dev = device if device is not None else torch.device("cpu")
+    owner = torch.zeros(n_units, dtype=torch.int64, device=dev)
+    sizes = torch.zeros(n_units, dtype=torch.int64, device=dev)
+    for i in mine:
+        owner[i] = rank; sizes[i] = len(local[i])
+    dist.all_reduce(owner); dist.all_reduce(sizes)
+    owner_h, sizes_h = owner.cpu().tolist(), sizes.cpu().tolist()
+    per_rank = [sum(sizes_h[i] for i in range(n_units) if owner_h[i] == r) for r in range(world)]
+    cap = max(max(per_rank), 1)
+    buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    blob = b"".join(local[i] for i in sorted(mine))
+    if blob:
+        buf[:len(blob)] = torch.from_numpy(np.frombuffer(blob, np.uint8).copy()).to(dev)
+    parts = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    if rank != 0:
+        return None
+    out = [None] * n_units
+    for r in range(world):
+        flat, off = parts[r].cpu().numpy(), 0
+        for i in range(n_units):
+            if owner_h[i] == r:
+                out[i] = flat[off:off + sizes_h[i]].tobytes(); off += sizes_h[i]
+    return out
+
+
+def main(argv=None):
+    import torch
+    import torch.distributed as dist
+    import sac_b200 as sb
+    argv = list(sys.argv[1:] if argv is None else argv)
+    out_dir, preset, gen, files = "sac_out", "normal", 0, []
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a == "--out": out_dir = argv[i + 1]; i += 1
+        elif a in ("--normal", "--high", "--veryhigh", "--extrahigh", "--best"): preset = a[2:]
+        elif a.startswith("--opt-cfg=dds,"): gen = int(a.split(",")[1])
+        else: files.append(a)
+        i += 1
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = sb.Engine(local)                              # raises without a GPU: no CPU fallback
+    cfg = sb.make_cfg(preset)
+    if gen:
+        cfg.num_threads = gen
+    cfg.frame_parallel = 2; cfg.reset = 1               # frames of a file in flight together (--opt-reset semantics)
+    rep, secs = encode_batch(files, out_dir, lambda wav: eng.encode_memory(cfg, wav)[0], rank, world, dev)
+    if rank == 0:
+        tot_in = sum(r[1] for r in rep); tot_out = sum(r[2] for r in rep)
+        print(json.dumps({"files": len(rep), "n_gpus": world, "in_bytes": tot_in, "out_bytes": tot_out, "seconds": round(secs, 3),
+                          "msamples_per_s": round((tot_in - 44 * len(rep)) / 4 / secs / 1e6, 5)}))
+    eng.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,3 +97,54 @@ def test_two_rank_candidate_sharded_search_is_the_single_rank_search():
         for r in range(2):
             assert res[r][1][k] == (float(best), xb.tobytes())       # every rank ends with the single-rank result, bit for bit
     assert res[0][2] + res[1][2] == total and abs(res[0][2] - res[1][2]) <= 12   # the work was split, nothing evaluated twice
+
+
+def _batch_worker(rank, world, port, q, paths, out_dir):
+    sys.path.insert(0, ROOT)
+    import zlib
+    import torch.distributed as dist
+    from sac_b200 import batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    done = []
+
+    def fake_encode(wav):                       # the encoder needs a GPU; the plumbing does not care what the bytes are
+        done.append(len(wav))
+        return b"SAC2" + zlib.compress(wav, 1)
+
+    rep, secs = batch.encode_batch(paths, out_dir, fake_encode, rank, world)
+    q.put((rank, done, rep, secs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_file_batch(tmp_path):
+    """configs[3] plumbing: files dealt by size, encoded per rank, gathered once, written by rank 0 in input order"""
+    import zlib
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from sac_b200 import batch
+    rng = np.random.default_rng(3)
+    sizes = [5000, 12000, 700, 9000, 9000, 300, 15001]
+    paths = []
+    for i, n in enumerate(sizes):
+        p = str(tmp_path / ("f%d.wav" % i))
+        open(p, "wb").write(rng.integers(0, 40, n).astype(np.uint8).tobytes())
+        paths.append(p)
+    plan = batch.assign_files(sizes, 2)
+    assert sorted(plan[0] + plan[1]) == list(range(7))
+    assert abs(sum(sizes[i] for i in plan[0]) - sum(sizes[i] for i in plan[1])) <= 1000     # balanced by bytes, not by count
+    out_dir = str(tmp_path / "out")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_batch_worker, args=(r, 2, port, q, paths, out_dir)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda x: x[0])
+    for p in procs: p.join(60)
+    assert sorted(res[0][1]) == sorted(sizes[i] for i in plan[0]) and sorted(res[1][1]) == sorted(sizes[i] for i in plan[1])
+    assert res[1][2] is None and [r[1] for r in res[0][2]] == sizes
+    for i, p in enumerate(paths):
+        img = open(os.path.join(out_dir, "f%d.sac" % i), "rb").read()
+        assert img[:4] == b"SAC2" and zlib.decompress(img[4:]) == open(p, "rb").read()
+    assert res[0][3] == res[1][3] > 0
