@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -175,35 +176,79 @@ int main(int argc, const char *argv[])
     std::printf("\n  Time:    [00:00:00]\n");                          // cmdline.cpp:355-356
     return rc;
   }
-  sac_engine *eng = sac_engine_create(gpu);
-  if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
+  // console output mirrors CmdLine::Process (cmdline.cpp:245-358): Open / PrintWav / Create / PrintMode / MD5 / ratio line
+  const auto t_all = std::chrono::steady_clock::now();
+  std::vector<uint8_t> img;
+  std::cout << "Open: '" << in << "': ";
+  {
+    std::ifstream f(in, std::ios::binary);
+    if (!f) { std::cout << "could not open\n"; return 1; }
+    img.assign((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  }
+  std::cout << "ok (" << img.size() << " Bytes)\n";
   sac_file_stats st;
+  std::memset(&st, 0, sizeof(st));
   int rc;
+  sac_engine *eng = nullptr;
   if (mode == ENCODE) {
-    std::cout << "Open: '" << in << "'\nCreate: '" << out << "'\n";
-    std::printf("  Profile: %ds%s%s\n", cfg.max_framelen, cfg.zero_mean ? " zero-mean" : "", cfg.frame_parallel ? " frame-parallel" : "");
+    // host half first (WAV parse, header, MD5, frame plan: no GPU involved), so that a bad input is reported as the reference does
+    if (sac_container_plan(&cfg, img.data(), (long long)img.size(), nullptr, 0, nullptr, nullptr, 0, &st)) {
+      const std::string err = sac_last_error();
+      if (err.find("unsupported input format") != std::string::npos) {
+        std::printf("  WAVE  Codec: PCM\n");
+        std::cerr << "unsupported input format\nmust be 1-16 bit, mono/stereo, pcm\n";                 // cmdline.cpp:253-262
+      } else std::cout << "warning: input is not a valid .wav file\n";
+      return 1;
+    }
+    std::printf("  WAVE  Codec: PCM (%d kbps)\n  %dHz %d Bit  %s\n  %d Samples [%s]\n", (st.samplerate * st.nch * st.bits) / 1000, st.samplerate,
+                st.bits, st.nch == 1 ? "Mono" : "Stereo", st.numsamples, time_str(st.numsamples, st.samplerate).c_str());
+    eng = sac_engine_create(gpu);
+    if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
+    std::cout << "Create: '" << out << "': ";
+    { std::ofstream probe(out, std::ios::binary); if (!probe) { std::cout << "could not create\n"; sac_engine_destroy(eng); return 1; } }
+    std::cout << "ok\n";
+    std::printf("  Profile: mt%d %ds%s%s%s\n", mt_mode, cfg.max_framelen, cfg.adapt_block ? " ab" : "", cfg.zero_mean ? " zero-mean" : "",
+                cfg.sparse_pcm ? " sparse-pcm" : "");
     if (cfg.optimize) {
       const char *cs[] = {"L1", "rms", "ent", "glb", "bpn"};
-      std::printf("  Optimize: %s %.1f%%,n=%d,%s,k=%d,gen=%d\n", cfg.search == SAC_SEARCH_DE ? "DE" : (cfg.search == SAC_SEARCH_CMA ? "CMA" : "DDS"),
-                  cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk, cfg.search == SAC_SEARCH_DE ? 30 : cfg.num_threads);
+      std::printf("  Optimize: %s %.1f%%,n=%d,%s,k=%d\n", cfg.search == SAC_SEARCH_DE ? "DE" : (cfg.search == SAC_SEARCH_CMA ? "" : "DDS"),
+                  cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk);
     }
+    if (cfg.frame_parallel || (cfg.optimize && cfg.num_threads > 0))                                     // not in the reference: how the GPU is fed
+      std::printf("  B200: generation %d, frame-parallel %d, gpu %d\n", cfg.search == SAC_SEARCH_DE ? 30 : cfg.num_threads, cfg.frame_parallel, gpu);
+    std::printf("\n");
     rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
     if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
-    std::printf("  %dHz %d Bit  %s  %d Samples [%s]\n", st.samplerate, st.bits, st.nch == 1 ? "Mono" : "Stereo", st.numsamples,
-                time_str(st.numsamples, st.samplerate).c_str());
+    std::printf("  %d/%d: 100.0%%\n", st.numsamples, st.numsamples);
     std::printf("  MD5:     "); print_md5(st.md5); std::printf("\n");
     const double r = st.out_bytes * 100.0 / st.in_bytes, bps = (st.out_bytes * 8.) / ((double)st.numsamples * st.nch);
     const double xr = st.seconds > 0 ? (st.numsamples / (double)st.samplerate) / st.seconds : 0.0;
     std::printf("\n  %lld->%lld=%.1f%% (%.3f bps)  %.3fx\n", st.in_bytes, st.out_bytes, r, bps, xr);
   } else {
-    std::cout << "Open: '" << in << "'\nCreate: '" << out << "'\n";
+    if (img.size() < 38 || std::memcmp(img.data(), "SAC2", 4)) { std::cout << "warning: input is not a valid .sac file\n"; return 1; }
+    {
+      const int nch = rd16(&img[4]), sr = (int)rd32(&img[6]), bits = rd16(&img[10]), fl = img[16];
+      const uint32_t ns = rd32(&img[12]), md = rd32(&img[18]);
+      const double bps = (img.size() * 8.0) / ((double)ns * nch);
+      std::printf("  WAVE  Codec: PCM (%d kbps)\n  %dHz %d Bit  %s\n  %u Samples [%s]\n", (int)std::round((sr * nch * bps) / 1000), sr, bits,
+                  nch == 1 ? "Mono" : "Stereo", ns, time_str(ns, sr).c_str());
+      std::printf("  Profile: mt%d %ds\n  Ratio:   %.3f bps\n\n  Audio MD5: ", mt_mode, fl, bps);            // cmdline.cpp:307-311
+      if (22 + (size_t)md + 16 <= img.size()) print_md5(&img[22 + md]);
+      std::printf("\n");
+    }
+    eng = sac_engine_create(gpu);
+    if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
+    std::cout << "Create: '" << out << "': ";
     rc = sac_decode_file(eng, in.c_str(), out.c_str(), &st);
-    if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
+    if (rc) { std::cout << "could not create\n"; std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
+    std::cout << "ok\n";
+    std::printf("  %d/%d: 100.0%%\n", st.numsamples, st.numsamples);
     const double xr = st.seconds > 0 ? (st.numsamples / (double)st.samplerate) / st.seconds : 0.0;
     std::printf("\n  Speed %.3fx\n  Audio MD5: ", xr);
     if (st.md5_ok) std::printf("ok\n"); else { std::printf("Error ("); print_md5(st.md5); std::printf(")\n"); }
   }
-  std::printf("\n  Time:    [%02d:%02d:%02d]\n", (int)(st.seconds / 3600), (int)(st.seconds / 60) % 60, (int)st.seconds % 60);
+  st.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_all).count();
+  { const long long t = (long long)std::llround(st.seconds); std::printf("\n  Time:    [%02d:%02d:%02d]\n", (int)(t / 3600), (int)(t / 60) % 60, (int)(t % 60)); }
   sac_engine_destroy(eng);
   return rc ? 1 : 0;
 }

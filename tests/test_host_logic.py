@@ -187,3 +187,21 @@ def test_container_prefix_and_frame_plan_match_the_reference_cli():
         sb.container_plan(sb.make_cfg("normal"), bytes(bad))
     with pytest.raises(sb.SacError):
         sb.container_plan(sb.make_cfg("normal"), b"RIFF\x04\x00\x00\x00WAVX")
+
+
+def test_cli_encode_prints_the_reference_header_then_fails_loudly_without_a_gpu(tmp_path):
+    """`sac --encode` console layout follows CmdLine::Process (cmdline.cpp:245-262): the Open line and PrintWav come from the
+    host container plan; without a CUDA device the tool then stops with an error and exit code 1 (no CPU fallback)."""
+    import subprocess, sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_container import wav_case
+    wav = wav_case("pcm24_stereo_extensible")
+    (tmp_path / "a.wav").write_bytes(wav)
+    r = subprocess.run([os.path.join(ROOT, "sac_b200", "sac"), "--encode", "--best", "a.wav", "a.sac"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    lines = r.stdout.splitlines()
+    i = lines.index("Open: 'a.wav': ok (%d Bytes)" % len(wav))
+    assert lines[i + 1:i + 4] == ["  WAVE  Codec: PCM (2304 kbps)", "  48000Hz 24 Bit  Stereo", "  9600 Samples [00:00:00.200]"]   # as the reference prints
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "a.sac").exists()
