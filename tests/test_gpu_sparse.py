@@ -76,3 +76,19 @@ def test_sparse_pcm_off_and_wide_samples_stay_unmapped(engine):
     assert _block_flags(rec, 1)[0] >> 9 == 0
     dec, used = engine.frame_decode(1, rec, FS)
     assert used == len(rec) and np.array_equal(dec[0], wide[0])
+
+
+def test_whole_file_with_split_and_mapped_blocks_equals_the_restatement(engine):
+    """file level: WAV with a sparse stretch -> adaptive sub-frame split, one rank-mapped block; the .sac image equals the
+    host container plan + the restatement's frame records (canonical arithmetic) byte for byte, and decodes to the input.
+    The same assembly in the reference's arithmetic is byte-identical to the reference CLI's file
+    (tests/test_oracle_pin.py::test_whole_files_are_byte_identical_to_the_reference_cli)."""
+    from make_golden_files import wav_of
+    from helpers import oracle_file_image
+    wav = wav_of("mono_sparse_middle")
+    sac, st = engine.encode_memory(sb.make_cfg("normal"), wav)
+    want, flags = oracle_file_image(wav, (ol.ORDER_B200, ol.MATH_CANON))
+    assert flags == [0, 1, 0, 0] and st.nframes == 4
+    assert len(sac) == len(want) and sac == want
+    back, st2 = engine.decode_memory(sac, len(wav) + 64)
+    assert st2.md5_ok == 1 and back == wav

@@ -249,3 +249,40 @@ def test_sparse_pcm_frame_records_match_reference():
         nb0 = lib.saco_encode_frame2(c["nch"], len(s[0]), ol._p(s[0], ol._i32p), ol._p(s[1], ol._i32p) if c["nch"] > 1 else None,
                                      ol._p(prof, ol._f32p), cfg, 0, ol._p(out, ol._u8p), len(out), mapped)
         assert list(mapped)[:c["nch"]] == [0] * c["nch"] and (nb0 > nb) == any(x[5] for x in c["stats"])
+
+
+def test_file_level_frame_plan_and_mapped_blocks_match_the_reference_cli():
+    """whole files with sparse stretches: the host frame plan + the restatement's per-block mapped/unmapped choice equal what
+    the UNMODIFIED reference CLI wrote (frame lengths and `sparse_pcm:` flags of --listfull; tests/golden/make_golden_split.py)"""
+    import io, json, sys, wave
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_split import case_pcm
+    from helpers import oracle_file_image
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_split.json")))
+    for name in ("mono_sparse_middle", "stereo_sparse_tail"):
+        c = [x for x in g["cases"] if x["name"] == name][0]
+        pcm = case_pcm(c["nch"], c["sr"], c["secs"], c["seed"], [tuple(s) for s in c["sparse"]])
+        b = io.BytesIO()
+        with wave.open(b, "wb") as w:
+            w.setnchannels(c["nch"]); w.setsampwidth(2); w.setframerate(c["sr"]); w.writeframes(pcm.astype("<i2").tobytes())
+        img, flags = oracle_file_image(b.getvalue(), REF)
+        assert flags == c["sparse_pcm_flags"], (name, flags, c["sparse_pcm_flags"])
+        assert img[:4] == b"SAC2" and len(img) < len(b.getvalue())
+
+
+def test_whole_files_are_byte_identical_to_the_reference_cli():
+    """Whole .sac files: host container plan (product, sac_container_plan) + the restatement's frame records (reference
+    order, libm) == the file the UNMODIFIED reference CLI (built with -ffp-contract=off) wrote, byte for byte: adaptive
+    sub-frame split, rank-mapped blocks, --sparse-pcm=0, DDS searches (sequential and population) warm-started from frame to
+    frame (tests/golden/make_golden_files.py)."""
+    import hashlib, json, sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_files import FILES, wav_of
+    from helpers import oracle_file_image
+    g = {f["name"]: f for f in json.load(open(os.path.join(ROOT, "tests", "golden", "golden_files.json")))["files"]}
+    assert len(g) == len(FILES) >= 6
+    for f in FILES:
+        wav = wav_of(f["src"])
+        assert hashlib.sha1(wav).hexdigest() == g[f["name"]]["wav_sha1"]
+        img, _ = oracle_file_image(wav, REF, sparse=f.get("sparse", 1), optimize=f["optimize"])
+        assert len(img) == g[f["name"]]["sac_len"] and hashlib.sha1(img).hexdigest() == g[f["name"]]["sac_sha1"], f["name"]
