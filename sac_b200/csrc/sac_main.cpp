@@ -28,11 +28,12 @@ static const char kHelp[] =
     "     no|s,n,c,k       s=[0,1.0],n=[0,10000]\n"
     "                      c=[l1,rms,glb,ent,bpn] k=[1,32]\n"
     "   --opt-cfg=#        configure optimization method\n"
-    "     dds,nt,s         nt=generation size (GPU batch),s=search radius (def=0.2)\n"
+    "     dds|de|cma,nt,s  nt=generation size (GPU batch; dds default 128, 0 = the reference's\n"
+    "                      sequential search), s=search radius (def=0.2)\n"
     "   --opt-reset        reset opt params at frame boundaries\n"
     "   --mt-mode=n        accepted, ignored (parallelism is the GPU's)\n"
     "   --zero-mean        zero-mean input\n"
-    "   --adapt-block      accepted (adaptive splitting not implemented)\n"
+    "   --adapt-block      adaptive frame splitting (default), --adapt-block=no disables it\n"
     "   --framelen=n       def=20 seconds\n"
     "   --sparse-pcm       enable pcm modelling (default), --sparse-pcm=no disables it\n"
     "  B200 options\n"
@@ -113,6 +114,7 @@ int main(int argc, const char *argv[])
   bool first = true;
   int gpu = 0;
   int mt_mode = 2;                                                    // tsac_cfg default (libsac.h:19-44); listings echo it
+  bool gen_given = false;                                             // --opt-cfg=...,N seen
   for (int k = 1; k < argc; k++) {
     const std::string param = argv[k];
     const std::string up = upper(param);
@@ -159,7 +161,7 @@ int main(int argc, const char *argv[])
           else if (vs[0] == "CMA") cfg.search = SAC_SEARCH_CMA;
           else std::cerr << "  warning: invalid opt='" << vs[0] << "'\n";
         }
-        if (vs.size() >= 2) cfg.num_threads = std::clamp(std::atoi(vs[1].c_str()), 0, 4096);
+        if (vs.size() >= 2) { cfg.num_threads = std::clamp(std::atoi(vs[1].c_str()), 0, 4096); gen_given = true; }
         if (vs.size() >= 3) cfg.sigma = std::clamp(std::atof(vs[2].c_str()), 0., 1.);
       } else if (key == "--ADAPT-BLOCK") cfg.adapt_block = !(val == "NO" || val == "0");
       else if (key == "--ZERO-MEAN") cfg.zero_mean = !(val == "NO" || val == "0");
@@ -176,6 +178,10 @@ int main(int argc, const char *argv[])
     std::printf("\n  Time:    [00:00:00]\n");                          // cmdline.cpp:355-356
     return rc;
   }
+  // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step, which
+  // on a GPU is one chain per launch. Unless the user says otherwise the DDS search therefore runs the reference's own
+  // population variant (OptDDS::run_mt, dds.cpp:63-106) with generations of 128; --opt-cfg=dds,0 restores the sequential one.
+  if (mode == ENCODE && cfg.optimize && cfg.search == SAC_SEARCH_DDS && !gen_given) cfg.num_threads = 128;
   // console output mirrors CmdLine::Process (cmdline.cpp:245-358): Open / PrintWav / Create / PrintMode / MD5 / ratio line
   const auto t_all = std::chrono::steady_clock::now();
   std::vector<uint8_t> img;
