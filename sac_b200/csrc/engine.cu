@@ -131,7 +131,7 @@ Engine *Engine::helper(int i)
 long long Engine::total_launches() const
 {
   long long t = launches;
-  for (const Engine *h : helpers) t += h->launches;
+  for (const Engine *h : helpers) t += h->total_launches();          // helpers of helpers run the final passes of frames in flight
   return t;
 }
 
