@@ -67,6 +67,8 @@ CASES = {
                                     after=[("id3 ", "tag-bytes-odd"), ("bext", "even")]),
     "truncated_data": dict(sr=44100, nch=2, width=2, secs=0.2, seed=76, fmt=16, declare_extra=4000),
     "three_frames_8k": dict(sr=8000, nch=1, width=2, secs=45.0, seed=77, fmt=16),
+    "empty_data": dict(sr=44100, nch=2, width=2, secs=0.0, seed=78, fmt=16),
+    "one_sample": dict(sr=44100, nch=1, width=2, secs=1.0 / 44100, seed=79, fmt=16),
 }
 
 
