@@ -57,7 +57,17 @@ double saco_dds_run(int ndim, const double *xmin, const double *xmax, const doub
  * out = profile used. cfg: {optimize, fraction*1e6, maxnfunc, num_threads, sigma*1e6, optk, cost_kind, max_framesize} */
 int saco_encode_frame(int nch, int n, const int32_t *s0, const int32_t *s1, float *profile_io, const int *cfg,
                       uint8_t *out, int cap);
-/* inverse: parses one frame record, returns bytes consumed; samples (mean restored) to s0[, s1]; n to *n_out */
+/* same with the sparse-PCM choice explicit (tsac_cfg::sparse_pcm, libsac.h:34; saco_encode_frame uses the default 1):
+ * a channel is coded rank-mapped when sum|e| / sum|Map(e)| > 1.05 and the mapped record is shorter (libsac.cpp:253-278);
+ * mapped_out[ch] (optional) tells which. */
+int saco_encode_frame2(int nch, int n, const int32_t *s0, const int32_t *s1, float *profile_io, const int *cfg,
+                       int sparse_pcm, uint8_t *out, int cap, int *mapped_out);
+/* sparse-PCM pieces (libsac/map.cpp): the coded used-value map of raw samples (Remap::Analyse + MapEncoder::Encode),
+ * its decoder (flags by magnitude, [32769] each), and Remap::Map / Unmap element-wise against the map of `raw` */
+int saco_map_encode(const int32_t *raw, int n, uint8_t *out, int cap);
+void saco_map_decode(const uint8_t *in, int nbytes, uint8_t *usedl, uint8_t *usedh);
+void saco_remap(const int32_t *raw, int nraw, const int32_t *pred, const int32_t *err, int n, int unmap, int32_t *out);
+/* inverse: parses one frame record (mapped blocks included), returns bytes consumed; samples (mean restored) to s0[, s1] */
 int saco_decode_frame(int nch, const uint8_t *in, int len, int32_t *s0, int32_t *s1, int *n_out);
 
 #ifdef __cplusplus
