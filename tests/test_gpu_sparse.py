@@ -92,3 +92,23 @@ def test_whole_file_with_split_and_mapped_blocks_equals_the_restatement(engine):
     assert len(sac) == len(want) and sac == want
     back, st2 = engine.decode_memory(sac, len(wav) + 64)
     assert st2.md5_ok == 1 and back == wav
+
+
+def test_cli_encode_decode_roundtrip_and_console_layout(tmp_path):
+    """the `sac` CLI end to end on the GPU: encode (DDS in generations, the CLI's default), decode, cmp; console lines follow
+    CmdLine::Process (cmdline.cpp:245-358)"""
+    import re
+    import subprocess
+    from make_golden_container import wav_case
+    cli = os.path.join(ROOT, "sac_b200", "sac")
+    wav = wav_case("chunks_before_and_after")                      # stereo 32 kHz, LIST/fact before and id3/bext after 'data'
+    (tmp_path / "a.wav").write_bytes(wav)
+    r = subprocess.run([cli, "--encode", "--optimize=0.05,9,ent", "a.wav", "a.sac"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    assert "Open: 'a.wav': ok (%d Bytes)" % len(wav) in out and "  32000Hz 16 Bit  Stereo\n  8000 Samples [00:00:00.250]\n" in out
+    assert "Create: 'a.sac': ok\n  Profile: mt2 20s ab zero-mean sparse-pcm\n  Optimize: DDS 5.0%,n=9,ent,k=4\n" in out
+    assert re.search(r"\n  MD5:     [0-9a-f]+\n\n  %d->\d+=\d+\.\d%% \(\d+\.\d{3} bps\)  \d+\.\d{3}x\n\n  Time:    \[\d\d:\d\d:\d\d\]\n$" % len(wav), out), out
+    r = subprocess.run([cli, "--decode", "a.sac", "b.wav"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Create: 'b.wav': ok\n" in r.stdout and "  Audio MD5: ok\n" in r.stdout, r.stdout + r.stderr
+    assert (tmp_path / "b.wav").read_bytes() == wav
