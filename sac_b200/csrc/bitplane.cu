@@ -259,7 +259,11 @@ __device__ __forceinline__ uint32_t counter_upd_s(const uint16_t *divtab, uint32
 }
 
 constexpr int kPipeThreads = 128;                                  // threads per stream (4 pipeline warps)
-constexpr int kPipeStreams = 2;                                    // streams per CTA: they share the 72 KB of LogDomain tables
+#ifndef SACB_PIPE_STREAMS
+#define SACB_PIPE_STREAMS 2
+#endif
+constexpr int kPipeStreams = SACB_PIPE_STREAMS;                    // streams per CTA: they share the 72 KB of LogDomain tables (make EXTRA=-DSACB_PIPE_STREAMS=n to experiment)
+static_assert(kPipeStreams >= 1 && kPipeStreams <= 7, "named barriers 1..7 and 227 KB of shared memory bound the streams per CTA");
 
 template <int MODE>
 __global__ void __launch_bounds__(kPipeThreads * kPipeStreams) bitplane_pipe_kernel(const BpJob *__restrict__ jobs, int njobs, Tables TG)
