@@ -12,5 +12,8 @@ case "$1" in
   sweep8)  $G --gpus 8 --timeout 600 -- 'timeout 580 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tools/sweep_probe.py --pops 512,1024,2048,4096 > gpurun_out/sweep_n8.jsonl 2>&1; cat gpurun_out/sweep_n8.jsonl' ;;
   batch8)  $G --gpus 8 --timeout 900 -- 'python tools/make_corpus.py /tmp/c4 0.25 && timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29545 -m sac_b200.batch --best --opt-cfg=dds,128 --out /tmp/c4out /tmp/c4/*.wav 2>&1 | tail -5' ;;
   sparse)  $G --timeout 300 -- 'timeout 280 python -m pytest tests/test_gpu_sparse.py -q --durations=5 2>&1 | tail -12' ;;
-  *) echo "usage: $0 suite|bench|scale|sweep1|sweep8|batch8|sparse" ;;
+  streams) # bitplane streams per CTA: rebuild here, measure one default-profile generation + the coder's parity tests on the box
+           for n in 4 6 7 2; do touch sac_b200/csrc/bitplane.cu; make -s -C sac_b200/csrc EXTRA=-DSACB_PIPE_STREAMS=$n;
+             $G --timeout 300 -- "echo streams=$n; timeout 120 python tools/first_light.py 2>&1 | tail -4; timeout 150 python -m pytest tests/test_gpu_parity.py -q -k 'bitplane or frame_record or eval_population' 2>&1 | tail -3"; done ;;
+  *) echo "usage: $0 suite|bench|scale|sweep1|sweep8|batch8|sparse|streams" ;;
 esac
