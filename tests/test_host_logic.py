@@ -205,3 +205,23 @@ def test_cli_encode_prints_the_reference_header_then_fails_loudly_without_a_gpu(
     i = lines.index("Open: 'a.wav': ok (%d Bytes)" % len(wav))
     assert lines[i + 1:i + 4] == ["  WAVE  Codec: PCM (2304 kbps)", "  48000Hz 24 Bit  Stereo", "  9600 Samples [00:00:00.200]"]   # as the reference prints
     assert r.returncode == 1 and "no CPU fallback" in r.stderr and not (tmp_path / "a.sac").exists()
+
+
+def test_recorded_bench_lines_follow_the_contract():
+    """the bench lines kept under profiles/ carry every key of the bench.py contract (metric of BASELINE.json, roofline,
+    cpu_baseline, e2e with the copied bytes, clocks, launch count)"""
+    import json
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    for fn in ("bench_r1_n1.json", "bench_r1_n2_nfunc129.json"):
+        d = json.load(open(os.path.join(ROOT, "profiles", fn)))
+        assert d["metric"].split(";")[0] in base["metric"] and d["unit"] == "MSamples/s" and d["higher_is_better"] is True
+        for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches"):
+            assert k in d, (fn, k)
+        assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
+        assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["value"] > 0
+        assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if d["n_gpus"] == 1:
+            assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
