@@ -54,14 +54,33 @@ std::vector<double> DdsSearch::candidate(int nfunc)                     // dds.c
 void DdsSearch::propose(std::vector<std::vector<double>> &cands)
 {
   cands.clear();
-  if (!started_) { cands.push_back(xb_); pending_ = cands; return; }
+  if (!started_) {
+    cands.push_back(xb_);
+    pending_.clear();
+    if (num_threads_ > 0) {
+      // run_mt draws its first generation from the start vector, sigma_init and the evaluation counter alone
+      // (dds.cpp:66-83): none of it depends on f(xstart), which the selection only needs afterwards (dds.cpp:88-98).
+      // The start vector and the first generation therefore go out as ONE batch -- same candidates, same random draws,
+      // same selection, one launch set less per frame.
+      nfunc_ = 1;
+      const int nt = std::min(nfunc_max_ - nfunc_, num_threads_);
+      for (int i = 0; i < nt; i++) { pending_.push_back(candidate(nfunc_)); nfunc_++; }
+      cands.insert(cands.end(), pending_.begin(), pending_.end());
+    }
+    return;
+  }
   const int nt = num_threads_ <= 0 ? 1 : std::min(nfunc_max_ - nfunc_, num_threads_);
   for (int i = 0; i < nt; i++) { cands.push_back(candidate(nfunc_)); nfunc_++; }
   pending_ = cands;
 }
 void DdsSearch::consume(const double *costs)
 {
-  if (!started_) { fb_ = costs[0]; nfunc_ = 1; started_ = true; return; }
+  if (!started_) {
+    fb_ = costs[0]; started_ = true;
+    if (num_threads_ <= 0) { nfunc_ = 1; return; }
+    costs += 1;                                                        // the first generation travelled with the start vector
+    if (pending_.empty()) return;
+  }
   const int nt = (int)pending_.size();
   if (num_threads_ <= 0) {                                              // run_single + SSC0 (ssc.h:6-37)
     const bool ok = costs[0] < fb_;

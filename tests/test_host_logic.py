@@ -225,3 +225,44 @@ def test_recorded_bench_lines_follow_the_contract():
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         if d["n_gpus"] == 1:
             assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_dds_first_generation_travels_with_the_start_vector_and_nothing_else_changes():
+    """population DDS: the product sends the start vector and the first generation as ONE batch (run_mt's first generation
+    does not depend on f(xstart), dds.cpp:66-83). Evaluated points IN ORDER, incumbent and cost equal the restatement's
+    OptDDS (which evaluates them one after the other as the reference does), also for degenerate budgets."""
+    vmin, vmax, vdef = sb.base_profile()
+    idx = list(sb.SEARCH_DIMS)
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    D = len(xs)
+    lib = ol.oracle()
+
+    def obj(x):
+        z = (x - xmin) / (xmax - xmin)
+        return float(np.sum((z - 0.41) ** 2) + 0.07 * np.sum(np.cos(11 * z)))
+
+    for nfunc, nt, sigma in ((1, 4, 0.25), (2, 4, 0.25), (5, 8, 0.2), (33, 8, 0.25), (64, 64, 0.25), (130, 128, 0.25), (50, 0, 0.2)):
+        otrace = []
+
+        def cb(xp, n, _u):
+            x = np.ctypeslib.as_array(xp, shape=(n,)).copy()
+            otrace.append(x)
+            return obj(x)
+
+        fn = ol.COST_CB(cb)
+        oxb = np.zeros(D)
+        ofb = lib.saco_dds_run(D, ol._p(xmin, ol._f64p), ol._p(xmax, ol._f64p), ol._p(xs, ol._f64p), nfunc, nt, sigma, fn, None, ol._p(oxb, ol._f64p))
+        trace, batches = [], []
+
+        def f(X):
+            batches.append(len(X))
+            trace.extend(list(X))
+            return [obj(x) for x in X]
+
+        best, xb = sb.dds_run(f, xmin, xmax, xs, nfunc, nt, sigma)
+        assert len(trace) == len(otrace) == max(nfunc, 1) and all(np.array_equal(a, b) for a, b in zip(trace, otrace)), (nfunc, nt)
+        assert best == ofb and np.array_equal(xb, oxb), (nfunc, nt)
+        if nt > 0:
+            assert batches[0] == 1 + min(nfunc - 1, nt) and sum(batches) == nfunc      # one launch set fewer than generations + 1
+        else:
+            assert batches == [1] * nfunc
