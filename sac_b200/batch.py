@@ -4,7 +4,7 @@ encodes its files on its own GPU with no data-path collective, the .sac images t
 (sac_b200/shard.py) and rank 0 writes them. The reference's equivalent is one `sac --encode` process per file.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \\
-        -m sac_b200.batch --best --opt-cfg=dds,128 --out outdir a.wav b.wav ...
+        -m sac_b200.batch --best --opt-cfg=dds,128 --files-in-flight=2 --out outdir a.wav b.wav ...
 """
 import json
 import os
@@ -26,17 +26,51 @@ def assign_files(sizes, world):
 
 
 def encode_batch(paths, out_dir, encode_fn, rank=0, world=1, device=None):
-    """encode_fn(wav_bytes) -> sac_bytes (this rank's GPU). Every rank must call this with the same `paths`.
+    """encode_fn(wav_bytes) -> sac_bytes (this rank's GPU), or a list of such callables = that many files in flight on
+    this GPU (one engine each). Every rank must call this with the same `paths`.
     Returns on rank 0: [(path, in_bytes, out_bytes)] in input order, and the seconds of the slowest rank (device-timed by
     the caller's encode_fn; here: wall around this rank's files, max over ranks)."""
     from . import shard
     sizes = [os.path.getsize(p) for p in paths]
     mine = assign_files(sizes, world)[rank]
+    fns = list(encode_fn) if isinstance(encode_fn, (list, tuple)) else [encode_fn]
     t0 = time.perf_counter()
     local = {}
-    for i in mine:
+
+    def one(i, fn):
         with open(paths[i], "rb") as f:
-            local[i] = encode_fn(f.read())
+            return i, fn(f.read())
+
+    if len(fns) == 1:
+        for i in mine:
+            local[i] = one(i, fns[0])[1]
+    else:
+        # several files in flight on this GPU (one engine each): a file of one or two frames does not fill the machine.
+        # Longest files first; a worker takes the next file as soon as it is free.
+        import queue
+        import threading
+        todo = queue.Queue()
+        for i in sorted(mine, key=lambda k: (-sizes[k], k)):
+            todo.put(i)
+        errs = []
+
+        def work(fn):
+            while True:
+                try:
+                    i = todo.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    local[i] = one(i, fn)[1]
+                except Exception as e:          # surface the first failure on the calling thread
+                    errs.append(e)
+                    return
+
+        th = [threading.Thread(target=work, args=(fn,)) for fn in fns]
+        for t in th: t.start()
+        for t in th: t.join()
+        if errs:
+            raise errs[0]
     secs = shard.max_over_ranks(time.perf_counter() - t0, device)
     got = _gather(local, len(paths), mine, rank, world, device)
     if rank != 0:
@@ -89,13 +123,14 @@ def main(argv=None):
     import torch.distributed as dist
     import sac_b200 as sb
     argv = list(sys.argv[1:] if argv is None else argv)
-    out_dir, preset, gen, files = "sac_out", "normal", 0, []
+    out_dir, preset, gen, inflight, files = "sac_out", "normal", 0, 2, []
     i = 0
     while i < len(argv):
         a = argv[i]
         if a == "--out": out_dir = argv[i + 1]; i += 1
         elif a in ("--normal", "--high", "--veryhigh", "--extrahigh", "--best"): preset = a[2:]
         elif a.startswith("--opt-cfg=dds,"): gen = int(a.split(",")[1])
+        elif a.startswith("--files-in-flight="): inflight = int(a.split("=")[1])
         else: files.append(a)
         i += 1
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -103,17 +138,19 @@ def main(argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    eng = sb.Engine(local)                              # raises without a GPU: no CPU fallback
+    engines = [sb.Engine(local) for _ in range(max(1, inflight))]   # raises without a GPU: no CPU fallback
     cfg = sb.make_cfg(preset)
-    if gen:
-        cfg.num_threads = gen
+    if cfg.optimize:
+        cfg.num_threads = gen if gen else 128
     cfg.frame_parallel = 2; cfg.reset = 1               # frames of a file in flight together (--opt-reset semantics)
-    rep, secs = encode_batch(files, out_dir, lambda wav: eng.encode_memory(cfg, wav)[0], rank, world, dev)
+    fns = [(lambda wav, e=e: e.encode_memory(cfg, wav)[0]) for e in engines]
+    rep, secs = encode_batch(files, out_dir, fns, rank, world, dev)
     if rank == 0:
         tot_in = sum(r[1] for r in rep); tot_out = sum(r[2] for r in rep)
         print(json.dumps({"files": len(rep), "n_gpus": world, "in_bytes": tot_in, "out_bytes": tot_out, "seconds": round(secs, 3),
                           "msamples_per_s": round((tot_in - 44 * len(rep)) / 4 / secs / 1e6, 5)}))
-    eng.close()
+    for e in engines:
+        e.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
