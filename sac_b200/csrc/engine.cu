@@ -564,11 +564,43 @@ int sac_eval_jobs(sac_engine *h, int njobs, const sac_window *const *wins, const
       jobs[j].profile[idx] = (float)X[(size_t)j * D + i];           // vdef is a float (profile.h:70-72, libsac.cpp:394)
     }
   }
+  // Experiment switch (off by default, SACB_LPT=1): evaluate the jobs longest-expected-first. CTAs are dispatched in slot
+  // order = order of first appearance, so this lets the chains with thousands of taps / high OLS orders start first when
+  // the launch has more chains than resident CTA slots. Costs are scattered back to the caller's order; results are
+  // unaffected (every job is an independent computation).
+  static const bool lpt = [] { const char *v = std::getenv("SACB_LPT"); return v && v[0] == '1'; }();
+  std::vector<int> order;
+  std::vector<double> cost_sorted;
+  if (lpt && njobs > 1) {
+    std::vector<double> est(njobs);
+    for (int j = 0; j < njobs; j++) {
+      const HostParam hp = map_profile(jobs[j].profile);
+      double w = 0.0;
+      for (int cc = 0; cc < jobs[j].win->nch; cc++) {
+        const double no = (double)ols_order(hp, cc);
+        double taps = 0.0;
+        for (int s2 = 0; s2 < 4; s2++) taps += hp.vn[cc][s2];
+        w = std::max(w, (double)jobs[j].n * (taps / 128.0 + no * no * no / (8.0 * optk) + 40.0));   // the job ends with its slower channel
+      }
+      est[j] = w;
+    }
+    order.resize(njobs);
+    for (int j = 0; j < njobs; j++) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return est[a] > est[b]; });
+    std::vector<Job> sorted(njobs);
+    for (int i = 0; i < njobs; i++) sorted[i] = jobs[order[i]];
+    jobs.swap(sorted);
+    cost_sorted.resize(njobs);
+  }
   std::vector<int> cj, cc;
   size_t stride;
   int rc = e->run_predict(jobs, cj, cc, stride);
   if (rc) return rc;
-  return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
+  if (order.empty()) return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
+  rc = e->run_cost(cost_kind, jobs, cj, cc, stride, cost_sorted.data());
+  if (rc) return rc;
+  for (int i = 0; i < njobs; i++) cost[order[i]] = cost_sorted[i];
+  return SAC_OK;
 }
 
 int sac_eval_population(sac_engine *h, const sac_window *w, int from, int n, const float *base_profile, const int *dims, int D,

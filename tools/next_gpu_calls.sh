@@ -15,5 +15,6 @@ case "$1" in
   streams) # bitplane streams per CTA: rebuild here, measure one default-profile generation + the coder's parity tests on the box
            for n in 4 6 7 2; do touch sac_b200/csrc/bitplane.cu; make -s -C sac_b200/csrc EXTRA=-DSACB_PIPE_STREAMS=$n;
              $G --timeout 300 -- "echo streams=$n; timeout 120 python tools/first_light.py 2>&1 | tail -4; timeout 150 python -m pytest tests/test_gpu_parity.py -q -k 'bitplane or frame_record or eval_population' 2>&1 | tail -3"; done ;;
-  *) echo "usage: $0 suite|bench|scale|sweep1|sweep8|batch8|sparse|streams" ;;
+  lpt)     $G --timeout 400 -- 'for v in 0 1; do echo SACB_LPT=$v; SACB_LPT=$v timeout 170 python tools/gen_probe.py 20000 128 0.67 2>&1 | tail -4; done; SACB_LPT=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -k "eval_population or frame_record" 2>&1 | tail -3' ;;
+  *) echo "usage: $0 suite|bench|scale|sweep1|sweep8|batch8|sparse|streams|lpt" ;;
 esac
