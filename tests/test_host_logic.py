@@ -266,3 +266,34 @@ def test_dds_first_generation_travels_with_the_start_vector_and_nothing_else_cha
             assert batches[0] == 1 + min(nfunc - 1, nt) and sum(batches) == nfunc      # one launch set fewer than generations + 1
         else:
             assert batches == [1] * nfunc
+
+
+def test_product_search_driver_reaches_the_reference_frame_profile():
+    """FrameCoder::Optimize end to end on the CPU: the PRODUCT's DDS driver (population: start vector + first generation as one
+    batch; sequential) fed with the restatement's objective (PredictFrame k=4 + cost on the centred window, reference order
+    and libm) ends with exactly the 58 floats the reference's FrameCoder::Predict() ended with (tens of dimensions moved;
+    tests/golden/make_golden_search.py)."""
+    import hashlib, json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_search.json")))
+    vmin, vmax, vdef = ol.base_profile()
+    idx = list(sb.SEARCH_DIMS)
+    xmin = vmin[idx].astype(np.float64); xmax = vmax[idx].astype(np.float64); xs = vdef[idx].astype(np.float64)
+    from synth_wav import synth_pcm
+    for c in g["cases"]:
+        assert c["changed"] >= 20
+        kw = c["cfg"]
+        pcm = synth_pcm(c["secs"], c["nch"], c["seed"]).astype(np.int32)
+        planes, means, mm = ol.analyse([np.ascontiguousarray(pcm[:, ch]) for ch in range(c["nch"])])
+        n = len(pcm); nopt = min(n, int(np.ceil(20 * 44100 * kw["fraction"]))); start = (n - nopt) // 2      # libsac.cpp:367-371
+
+        def f(X):
+            out = []
+            for x in X:
+                prof = vdef.copy(); prof[idx] = x.astype(np.float32)                                      # libsac.cpp:394
+                e, _ = ol.oracle_predict(planes, mm, prof, 4, start, nopt, ol.ORDER_REF, ol.MATH_LIBM)
+                out.append(sum(ol.oracle_cost(kw["cost_kind"], ee, ol.MATH_LIBM) for ee in e))
+            return out
+
+        best, xb = sb.dds_run(f, xmin, xmax, xs, kw["maxnfunc"], kw["num_threads"], kw["sigma"])
+        prof = vdef.copy(); prof[idx] = xb.astype(np.float32)                                             # libsac.cpp:418-420
+        assert hashlib.sha1(prof.tobytes()).hexdigest() == c["profile_sha1"], c["name"]
