@@ -286,3 +286,25 @@ def test_whole_files_are_byte_identical_to_the_reference_cli():
         assert hashlib.sha1(wav).hexdigest() == g[f["name"]]["wav_sha1"]
         img, _ = oracle_file_image(wav, REF, sparse=f.get("sparse", 1), optimize=f["optimize"])
         assert len(img) == g[f["name"]]["sac_len"] and hashlib.sha1(img).hexdigest() == g[f["name"]]["sac_sha1"], f["name"]
+
+
+def test_frame_search_that_moves_matches_reference():
+    """saco_encode_frame with searches that change tens of dimensions (population and sequential DDS, L1 / entropy / bitplane
+    objectives): the profile written into the frame record equals the reference FrameCoder's (tests/golden/make_golden_search.py)"""
+    import hashlib, json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_search.json")))
+    lib = ol.oracle()
+    lib.saco_set_modes(*REF)
+    _, _, vdef = ol.base_profile()
+    for c in g["cases"]:
+        kw = c["cfg"]
+        pcm = synth_pcm(c["secs"], c["nch"], c["seed"]).astype(np.int32)
+        s = [np.ascontiguousarray(pcm[:, ch]) for ch in range(c["nch"])]
+        cfg = (C.c_int * 8)(1, int(round(kw["fraction"] * 1e6)), kw["maxnfunc"], kw["num_threads"], int(round(kw["sigma"] * 1e6)), 4, kw["cost_kind"],
+                            20 * 44100)
+        prof = vdef.copy()
+        out = np.zeros(8 * len(s[0]) + 4096, np.uint8)
+        nb = lib.saco_encode_frame(c["nch"], len(s[0]), ol._p(s[0], ol._i32p), ol._p(s[1], ol._i32p) if c["nch"] > 1 else None,
+                                   ol._p(prof, ol._f32p), cfg, ol._p(out, ol._u8p), len(out))
+        assert nb > 0 and hashlib.sha1(prof.tobytes()).hexdigest() == c["profile_sha1"], c["name"]
+        assert np.array_equal(np.frombuffer(out[4:4 + 58 * 4].tobytes(), np.float32), prof)
