@@ -87,6 +87,12 @@ int sac_cost(sac_engine *, int cost_kind, const int32_t *bufs, int count, int n,
 int sac_bitplane_encode(sac_engine *, const int32_t *resid, int n, int *maxbpn_io, uint8_t *out, long long cap, long long *out_len);
 int sac_bitplane_decode(sac_engine *, const uint8_t *payload, long long len, int n, int maxbpn, int32_t *resid_out);
 
+/* FrameCoder::SetParam (src/libsac/libsac.cpp:37-92) alone, host only: the 58 profile floats -> the predictor's parameters
+ * as this library hands them to its kernels. out[59] (doubles): nA,nB,nM0,nS0,nS1,ch_ref,lm_n,bias_scale | vn ch0[4],ch1[4] |
+ * vmu[2][4] | vmudecay[2][4] | vpowdecay[2][4] | lambda[2] | ols_nu[2] | mu_mix[2] | mu_mix_beta[2] |
+ * beta_sum,beta_pow,beta_add per channel | bias_mu[2] | lm_alpha | proj_alpha[2]. Returns 59. */
+int sac_profile_params(const float *profile58, double *out, int cap);
+
 /* ---- population evaluation -------------------------------------------------------------------------------------
  * cost[p] = sum over channels of Cost(PredictFrame(profile with dims[i] <- (float)X[p][i], window, k=optk)).
  * Non-finite predictor state gives cost = +INF. One call in flight per engine. */

@@ -213,6 +213,33 @@ void ref_remap(const int32_t *raw, int nraw, const int32_t *pred, const int32_t 
   for (int i = 0; i < n; i++) out[i] = unmap ? m.Unmap(pred[i], err[i]) : m.Map(pred[i], err[i]);
 }
 
+// FrameCoder::SetParam (libsac.cpp:37-92) flattened in the order of sac_profile_params (include/sac_b200.h)
+int ref_set_param(void *hp, const float *vdef, double *out)
+{
+  auto *h = static_cast<RefFrame *>(hp);
+  SacProfile prof = h->fc->base_profile;
+  for (size_t i = 0; i < prof.coefs.size(); i++) prof.coefs[i].vdef = vdef[i];
+  Predictor::tparam p;
+  h->fc->SetParam(p, prof, false);
+  int o = 0;
+  const int ints[8] = {p.nA, p.nB, p.nM0, p.nS0, p.nS1, p.ch_ref, p.lm_n, p.bias_scale0};
+  for (int v : ints) out[o++] = v;
+  for (int i = 0; i < 4; i++) out[o++] = p.vn0[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vn1[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vmu0[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vmu1[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vmudecay0[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vmudecay1[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vpowdecay0[i];
+  for (int i = 0; i < 4; i++) out[o++] = p.vpowdecay1[i];
+  out[o++] = p.lambda0; out[o++] = p.lambda1; out[o++] = p.ols_nu0; out[o++] = p.ols_nu1;
+  out[o++] = p.mu_mix0; out[o++] = p.mu_mix1; out[o++] = p.mu_mix_beta0; out[o++] = p.mu_mix_beta1;
+  out[o++] = p.beta_sum0; out[o++] = p.beta_pow0; out[o++] = p.beta_add0;
+  out[o++] = p.beta_sum1; out[o++] = p.beta_pow1; out[o++] = p.beta_add1;
+  out[o++] = p.bias_mu0; out[o++] = p.bias_mu1; out[o++] = p.lm_alpha; out[o++] = p.proj_alpha0; out[o++] = p.proj_alpha1;
+  return o;
+}
+
 // ---- cost functions (src/libsac/cost.h) ----------------------------------------------------------------------
 double ref_cost(int kind, const int32_t *buf, int n)
 {

@@ -188,6 +188,16 @@ def cma_run(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.0):
     return de_run(func, xmin, xmax, xstart, nfunc_max, sigma_init, entry="sac_cma_run")
 
 
+def profile_params(profile58):
+    """host-only: FrameCoder::SetParam as this library maps a profile (59 doubles, order in include/sac_b200.h)"""
+    prof = np.ascontiguousarray(profile58, np.float32)
+    out = np.zeros(64, np.float64)
+    n = lib().sac_profile_params(_p(prof, _f32p), _p(out, _f64p), 64)
+    if n < 0:
+        raise SacError("sac_profile_params failed: %s" % lib().sac_last_error().decode())
+    return out[:n]
+
+
 def container_plan(cfg, wav_bytes, cap_frames=4096):
     """host-only: (.sac bytes preceding the first frame record, [samples per frame record], FileStats)"""
     wav = np.frombuffer(wav_bytes, np.uint8)

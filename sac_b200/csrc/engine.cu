@@ -603,6 +603,28 @@ int sac_eval_jobs(sac_engine *h, int njobs, const sac_window *const *wins, const
   return SAC_OK;
 }
 
+int sac_profile_params(const float *profile58, double *out, int cap)
+{
+  if (!profile58 || !out || cap < 59) { set_error("sac_profile_params: bad argument"); return SAC_E_ARG; }
+  const HostParam p = map_profile(profile58);
+  int o = 0;
+  const int ints[8] = {p.nA, p.nB, p.nM0, p.nS0, p.nS1, p.ch_ref, p.lm_n, p.bias_scale};
+  for (int v : ints) out[o++] = v;
+  for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) out[o++] = p.vn[c][i];
+  for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) out[o++] = p.vmu[c][i];
+  for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) out[o++] = p.vmudecay[c][i];
+  for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) out[o++] = p.vpowdecay[c][i];
+  for (int c = 0; c < 2; c++) out[o++] = p.lambda[c];
+  for (int c = 0; c < 2; c++) out[o++] = p.ols_nu[c];
+  for (int c = 0; c < 2; c++) out[o++] = p.mu_mix[c];
+  for (int c = 0; c < 2; c++) out[o++] = p.mu_mix_beta[c];
+  for (int c = 0; c < 2; c++) { out[o++] = p.beta_sum[c]; out[o++] = p.beta_pow[c]; out[o++] = p.beta_add[c]; }
+  for (int c = 0; c < 2; c++) out[o++] = p.bias_mu[c];
+  out[o++] = p.lm_alpha;
+  for (int c = 0; c < 2; c++) out[o++] = p.proj_alpha[c];
+  return o;                                                          // 59
+}
+
 int sac_eval_population(sac_engine *h, const sac_window *w, int from, int n, const float *base_profile, const int *dims, int D,
                         const double *X, int P, int cost_kind, int optk, double *cost)
 {

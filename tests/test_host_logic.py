@@ -297,3 +297,20 @@ def test_product_search_driver_reaches_the_reference_frame_profile():
         best, xb = sb.dds_run(f, xmin, xmax, xs, kw["maxnfunc"], kw["num_threads"], kw["sigma"])
         prof = vdef.copy(); prof[idx] = xb.astype(np.float32)                                             # libsac.cpp:418-420
         assert hashlib.sha1(prof.tobytes()).hexdigest() == c["profile_sha1"], c["name"]
+
+
+def test_profile_mapping_equals_reference_setparam():
+    """FrameCoder::SetParam (SURVEY section 8 a2) as the product maps a profile for its kernels (sac_profile_params, host only)
+    against the reference's own SetParam for the default profile, random profiles in the search box, swapped channel order
+    and box corners: all 59 values bit for bit (tests/golden/make_golden_params.py)."""
+    import json, sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden_params import profiles
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_params.json")))["cases"]
+    vmin, vmax, vdef = sb.base_profile()
+    ps = profiles(vmin, vmax, vdef)
+    assert len(ps) == len(g) == 16
+    for p, want in zip(ps, g):
+        got = sb.profile_params(p)
+        assert len(got) == len(want) == 59
+        assert [float(x).hex() for x in got] == want
