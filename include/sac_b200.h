@@ -165,6 +165,9 @@ long long sac_frame_decode(sac_engine *, int nch, const uint8_t *in, long long l
 typedef struct sac_file_stats { long long in_bytes, out_bytes; int numsamples, nch, samplerate, bits, nframes; double seconds; uint8_t md5[16]; int md5_ok; } sac_file_stats;
 int sac_encode_file(sac_engine *, const sac_cfg *, const char *wav_path, const char *sac_path, sac_file_stats *);
 int sac_decode_file(sac_engine *, const char *sac_path, const char *wav_path, sac_file_stats *);
+/* Frame prologue of one channel (FrameCoder::AnalyseMonoChannel + zero-mean, libsac.cpp:626-651, 452-458), host only:
+ * out3 = {mean (0 when !zero_mean), min, max} with min/max taken after the mean is removed -- the block header's fields. */
+int sac_frame_stats(const int32_t *samples, int n, int zero_mean, int32_t *out3);
 /* Host part of Codec::EncodeFile alone (libsac.cpp:782-835; wav.cpp:167-263, sac.cpp:15-38; NO GPU needed): parses the
  * WAV image and writes what precedes the first frame record of the .sac file -- header, metadata (all WAV chunks), MD5 of
  * the PCM bytes -- to out[0,*out_len); frame_lengths[0,st->nframes) receives the samples per frame record (reads of

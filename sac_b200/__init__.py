@@ -198,6 +198,14 @@ def profile_params(profile58):
     return out[:n]
 
 
+def frame_stats(samples, zero_mean=1):
+    """host-only: (mean, min, max) of one channel as the block header carries them"""
+    s = np.ascontiguousarray(samples, np.int32)
+    out = np.zeros(3, np.int32)
+    _chk(lib().sac_frame_stats(_p(s, _i32p), len(s), int(zero_mean), _p(out, _i32p)), "sac_frame_stats")
+    return [int(x) for x in out]
+
+
 def container_plan(cfg, wav_bytes, cap_frames=4096):
     """host-only: (.sac bytes preceding the first frame record, [samples per frame record], FileStats)"""
     wav = np.frombuffer(wav_bytes, np.uint8)

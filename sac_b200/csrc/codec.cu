@@ -1363,6 +1363,14 @@ long long sac_frame_decode(sac_engine *h, int nch, const uint8_t *in, long long 
   return used;
 }
 
+int sac_frame_stats(const int32_t *samples, int n, int zero_mean, int32_t *out3)
+{
+  if (!samples || n <= 0 || !out3) { set_error("sac_frame_stats: bad argument"); return SAC_E_ARG; }
+  std::vector<int32_t> s(samples, samples + n);
+  analyse_channel(s, zero_mean, out3[0], out3[1], out3[2]);
+  return SAC_OK;
+}
+
 int sac_container_plan(const sac_cfg *cfg, const uint8_t *wav, long long wav_len, uint8_t *out, long long cap, long long *out_len,
                        int *frame_lengths, int cap_frames, sac_file_stats *st)
 {

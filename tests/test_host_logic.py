@@ -314,3 +314,25 @@ def test_profile_mapping_equals_reference_setparam():
         got = sb.profile_params(p)
         assert len(got) == len(want) == 59
         assert [float(x).hex() for x in got] == want
+
+
+def test_frame_prologue_stats_equal_the_reference():
+    """mean / min / max of a channel as the block header carries them (FrameCoder::AnalyseMonoChannel + zero-mean,
+    SURVEY section 8 a12): product host code against the reference's FrameCoder on awkward inputs -- negative and fractional
+    means (floor), constants, one sample, full-scale, with and without --zero-mean. Live against oracle/_ref when it is there,
+    and always against the formula the restatement uses (itself pinned through whole frame records)."""
+    rng = np.random.default_rng(7)
+    cases = [np.array([5], np.int32), np.array([-5], np.int32), np.array([-1, -2], np.int32), np.array([1, 2], np.int32),
+             np.full(1000, -32768, np.int32), np.full(999, 32767, np.int32), np.zeros(17, np.int32),
+             rng.integers(-32768, 32768, 4001).astype(np.int32), (rng.integers(-300, 100, 777) - 7).astype(np.int32),
+             rng.integers(-(1 << 23), 1 << 23, 513).astype(np.int32)]
+    ref = ol.ref_lib(nc=True)
+    for s in cases:
+        for zm in (1, 0):
+            got = sb.frame_stats(s, zm)
+            mean = int(np.floor(int(s.astype(np.int64).sum()) / float(len(s)))) if zm else 0
+            assert got == [mean, int(s.min()) - mean, int(s.max()) - mean]
+            if ref is not None:
+                rf = ol.RefFrame(ref, 1, 1 << 24, zero_mean=zm)
+                rf.set_samples([s]); rf.analyse()
+                assert rf.stats(0)[:3] == got, (len(s), zm)
