@@ -28,8 +28,8 @@ static const char kHelp[] =
     "     no|s,n,c,k       s=[0,1.0],n=[0,10000]\n"
     "                      c=[l1,rms,glb,ent,bpn] k=[1,32]\n"
     "   --opt-cfg=#        configure optimization method\n"
-    "     dds|de|cma,nt,s  nt=generation size (GPU batch; dds default 128, 0 = the reference's\n"
-    "                      sequential search), s=search radius (def=0.2)\n"
+    "     dds|de|cma,nt,s  nt=generation size (GPU batch; dds default: an eighth of the evaluation\n"
+    "                      budget, at most 128; 0 = the reference's sequential search), s=search radius (def=0.2)\n"
     "   --opt-reset        reset opt params at frame boundaries\n"
     "   --mt-mode=n        accepted, ignored (parallelism is the GPU's)\n"
     "   --zero-mean        zero-mean input\n"
@@ -180,8 +180,9 @@ int main(int argc, const char *argv[])
   }
   // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step, which
   // on a GPU is one chain per launch. Unless the user says otherwise the DDS search therefore runs the reference's own
-  // population variant (OptDDS::run_mt, dds.cpp:63-106) with generations of 128; --opt-cfg=dds,0 restores the sequential one.
-  if (mode == ENCODE && cfg.optimize && cfg.search == SAC_SEARCH_DDS && !gen_given) cfg.num_threads = 128;
+  // population variant (OptDDS::run_mt, dds.cpp:63-106) in about 8 generations (an eighth of the evaluation budget per
+  // generation, at most 128: --best -> 125, --high -> 13); --opt-cfg=dds,0 restores the sequential search.
+  if (mode == ENCODE && cfg.optimize && cfg.search == SAC_SEARCH_DDS && !gen_given) cfg.num_threads = std::clamp((cfg.maxnfunc + 7) / 8, 1, 128);
   // console output mirrors CmdLine::Process (cmdline.cpp:245-358): Open / PrintWav / Create / PrintMode / MD5 / ratio line
   const auto t_all = std::chrono::steady_clock::now();
   std::vector<uint8_t> img;
