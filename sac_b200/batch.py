@@ -141,7 +141,7 @@ def main(argv=None):
     engines = [sb.Engine(local) for _ in range(max(1, inflight))]   # raises without a GPU: no CPU fallback
     cfg = sb.make_cfg(preset)
     if cfg.optimize:
-        cfg.num_threads = gen if gen else 128
+        cfg.num_threads = gen if gen else min(128, max(1, (cfg.maxnfunc + 7) // 8))    # about 8 generations, as the CLI
     cfg.frame_parallel = 2; cfg.reset = 1               # frames of a file in flight together (--opt-reset semantics)
     fns = [(lambda wav, e=e: e.encode_memory(cfg, wav)[0]) for e in engines]
     rep, secs = encode_batch(files, out_dir, fns, rank, world, dev)
