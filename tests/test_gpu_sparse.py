@@ -90,6 +90,10 @@ def test_whole_file_with_split_and_mapped_blocks_equals_the_restatement(engine):
     want, flags = oracle_file_image(wav, (ol.ORDER_B200, ol.MATH_CANON))
     assert flags == [0, 1, 0, 0] and st.nframes == 4
     assert len(sac) == len(want) and sac == want
+    # ... and for this file that is the very file the reference CLI writes (tests/golden/golden_files.json)
+    import hashlib
+    gold = {f["name"]: f for f in json.load(open(os.path.join(ROOT, "tests", "golden", "golden_files.json")))["files"]}
+    assert hashlib.sha1(sac).hexdigest() == gold["mono_sparse_middle_normal"]["sac_sha1"]
     back, st2 = engine.decode_memory(sac, len(wav) + 64)
     assert st2.md5_ok == 1 and back == wav
 
