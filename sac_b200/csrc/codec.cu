@@ -390,7 +390,7 @@ int wav_parse(const uint8_t *f, size_t len, WavInfo &wi)
   size_t pos = 12;
   bool have_fmt = false, have_data = false;
   while (true) {
-    if (pos + 8 > len) { if (have_data) break; set_error("could not read wav chunk"); return SAC_E_FORMAT; }
+    if (pos + 8 > len) { set_error("could not read wav chunk"); return SAC_E_FORMAT; }   // also after 'data': stray bytes are an error (wav.cpp:182-183)
     const uint32_t id = get32(f + pos), cs = get32(f + pos + 4);
     pos += 8;
     if (id == kFMT) {

@@ -55,6 +55,7 @@ def wav_case(name):
         body += b"\0"
     for cid, payload in spec.get("after", []):
         body += _chunk(cid.encode(), payload.encode())
+    body += spec.get("stray", b"")
     return b"RIFF" + struct.pack("<I", len(body)) + body
 
 
@@ -69,6 +70,8 @@ CASES = {
     "three_frames_8k": dict(sr=8000, nch=1, width=2, secs=45.0, seed=77, fmt=16),
     "empty_data": dict(sr=44100, nch=2, width=2, secs=0.0, seed=78, fmt=16),
     "one_sample": dict(sr=44100, nch=1, width=2, secs=1.0 / 44100, seed=79, fmt=16),
+    "zero_length_chunk": dict(sr=44100, nch=2, width=2, secs=0.1, seed=80, fmt=16, before=[("LIST", "")], after=[("junk", "")]),
+    "stray_bytes_after_data": dict(sr=44100, nch=1, width=2, secs=0.1, seed=81, fmt=16, stray=b"\x01\x02\x03"),
 }
 
 
@@ -80,8 +83,15 @@ def main():
         for name in CASES:
             wav = wav_case(name)
             open(os.path.join(tmp, "a.wav"), "wb").write(wav)
+            if os.path.exists(os.path.join(tmp, "a.sac")):
+                os.remove(os.path.join(tmp, "a.sac"))
             r = subprocess.run([sac, "--encode", "--normal", "a.wav", "a.sac"], cwd=tmp, capture_output=True, text=True)
             assert r.returncode == 0, (name, r.stdout, r.stderr)
+            if not os.path.exists(os.path.join(tmp, "a.sac")):          # the reference refused the input
+                assert "not a valid .wav file" in r.stdout, (name, r.stdout)
+                out["cases"].append(dict(name=name, wav_sha1=hashlib.sha1(wav).hexdigest(), rejected=True))
+                print(name, len(wav), "-> rejected by the reference")
+                continue
             img = open(os.path.join(tmp, "a.sac"), "rb").read()
             mds = struct.unpack("<I", img[18:22])[0]
             prefix = img[:22 + mds + 16]
