@@ -108,6 +108,12 @@ int sac_eval_jobs(sac_engine *, int njobs, const sac_window *const *wins, const 
 typedef int (*sac_eval_fn)(const double *X, int P, int D, double *cost, void *user);
 double sac_dds_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
                    double sigma_init, sac_eval_fn eval, void *user, double *xbest);
+/* run_single (num_threads == 0, the reference's default search) in speculative batches: up to `spec` candidates per call of
+ * eval are drawn as run_single would draw them if each of them failed; costs are walked in order, the first success is
+ * applied, the generator rewound to that point and the rest of the batch dropped. Accepted sequence, step sizes and
+ * result equal sac_dds_run(..., num_threads = 0, ...); *evaluated (may be null) receives the candidates spent. */
+double sac_dds_run_spec(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
+                        int spec, sac_eval_fn eval, void *user, double *xbest, long long *evaluated);
 /* OptDE::run (src/opt/de.cpp:80-172; NP = 30, current-to-pbest/1/bin, adaptive CR and F) over the same evaluator seam:
  * the start vector, then the 29 initial samples, then generations of up to 30 trial vectors */
 double sac_de_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init,
@@ -141,6 +147,12 @@ typedef struct sac_cfg {        /* FrameCoder::tsac_cfg / toptim_cfg (src/libsac
                                    2 = every frame runs on its own stream / host thread, all concurrently on the GPU */
   int verbose;
   int search;                   /* SAC_SEARCH_*: --opt-cfg=dds|de|cma (src/cmdline.cpp:195-206) */
+  int spec;                     /* B200 extension, sequential DDS only (num_threads == 0, the reference's default): candidates per
+                                   speculative batch (sac_dds_run_spec). Results do not depend on it; 1 = one candidate per launch */
+  int inflight;                 /* frame_parallel == 2: frames in flight on the GPU (1..64) */
+  int grade;                    /* arithmetic of the SEARCH evaluations: 0 = canonical (bit-exact with the decoder's),
+                                   1 = search-grade kernels (same formulas, free summation order / fused operations; the final
+                                   pass and the bitstream are always canonical) */
 } sac_cfg;
 void sac_cfg_default(sac_cfg *);
 /* presets of src/cmdline.cpp:127-156: "normal","high","veryhigh","extrahigh","best","insane" */

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsac_b200.so")
+LIB_PATH = os.environ.get("SAC_B200_LIB") or os.path.join(_HERE, "libsac_b200.so")   # the override selects a build variant (tools/ probes)
 CLI_PATH = os.path.join(_HERE, "sac")
 
 PROFILE_SIZE = 58
@@ -37,7 +37,7 @@ class Cfg(C.Structure):
     _fields_ = [("optimize", C.c_int), ("fraction", C.c_double), ("maxnfunc", C.c_int), ("num_threads", C.c_int),
                 ("sigma", C.c_double), ("optk", C.c_int), ("cost_kind", C.c_int), ("reset", C.c_int), ("zero_mean", C.c_int),
                 ("sparse_pcm", C.c_int), ("max_framelen", C.c_int), ("adapt_block", C.c_int), ("frame_parallel", C.c_int),
-                ("verbose", C.c_int), ("search", C.c_int)]
+                ("verbose", C.c_int), ("search", C.c_int), ("spec", C.c_int), ("inflight", C.c_int), ("grade", C.c_int)]
 
 
 class FileStats(C.Structure):
@@ -84,6 +84,9 @@ def lib():
                                     C.c_int, C.c_int, _f64p]
         L.sac_dds_run.restype = C.c_double
         L.sac_dds_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
+        L.sac_dds_run_spec.restype = C.c_double
+        L.sac_dds_run_spec.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, C.c_int, EVAL_FN, C.c_void_p, _f64p,
+                                       C.POINTER(C.c_longlong)]
         L.sac_analyse_subframes.argtypes = [C.c_int, C.POINTER(_i32p), C.c_int, C.c_int, _intp, _intp, _intp, C.c_int]
         L.sac_de_run.restype = C.c_double
         L.sac_de_run.argtypes = [C.c_int, _f64p, _f64p, _f64p, C.c_int, C.c_double, EVAL_FN, C.c_void_p, _f64p]
@@ -151,6 +154,26 @@ def dds_run(func, xmin, xmax, xstart, nfunc_max, num_threads=0, sigma_init=0.2):
     best = lib().sac_dds_run(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, num_threads, sigma_init, fn, None,
                              _p(xbest, _f64p))
     return best, xbest
+
+
+def dds_run_spec(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.2, spec=16):
+    """run_single in speculative batches (host only): returns (best cost, best x, candidates evaluated)"""
+    xmin = np.ascontiguousarray(xmin, np.float64); xmax = np.ascontiguousarray(xmax, np.float64)
+    xstart = np.ascontiguousarray(xstart, np.float64)
+    D = len(xstart)
+    xbest = np.zeros(D)
+
+    def cb(Xp, P, Dd, costp, _user):
+        X = np.ctypeslib.as_array(Xp, shape=(P, Dd))
+        out = np.ctypeslib.as_array(costp, shape=(P,))
+        out[:] = np.asarray(func(X.copy()), np.float64)
+        return 0
+
+    fn = EVAL_FN(cb)
+    ev = C.c_longlong(0)
+    best = lib().sac_dds_run_spec(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, sigma_init, spec, fn, None,
+                                  _p(xbest, _f64p), C.byref(ev))
+    return best, xbest, int(ev.value)
 
 
 def analyse_subframes(planes, samplerate):

@@ -16,6 +16,7 @@
 #include <fstream>
 #include <limits>
 #include <array>
+#include <atomic>
 #include <memory>
 #include <string>
 #include <thread>
@@ -26,9 +27,9 @@ namespace sacb {
 // DDS
 // =====================================================================================================================
 DdsSearch::DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads,
-                     double sigma_init)
+                     double sigma_init, int spec)
     : D_(D), nfunc_max_(nfunc_max), num_threads_(num_threads), xmin_(xmin, xmin + D), xmax_(xmax, xmax + D), xb_(xstart, xstart + D),
-      sigma_(sigma_init)
+      sigma_(sigma_init), spec_(num_threads <= 0 ? std::max(spec, 1) : 1)
 {
 }
 double DdsSearch::reflect(double xnew, double lo, double hi) const      // opt.cpp:156-166
@@ -51,43 +52,92 @@ std::vector<double> DdsSearch::candidate(int nfunc)                     // dds.c
   }
   return xt;
 }
+void DdsSearch::ssc0_step(bool ok)                                      // SSC0(3,50)::update (ssc.h:6-37)
+{
+  if (ok) { nsucc_ += 1; nfail_ = 0; } else { nsucc_ = 0; nfail_ += 1; }
+  if (nsucc_ >= 3) { sigma_ = sigma_ * 2.0; nsucc_ = 0; } else if (nfail_ >= 50) { sigma_ = sigma_ / 2.0; nfail_ = 0; }
+  sigma_ = std::clamp(sigma_, 0.05, 0.5);
+}
+// Sequential search (run_single, dds.cpp:33-60) in speculative batches. A step of run_single draws its candidate from
+// (xb, sigma, nfunc, generator) and only then looks at the cost; most steps fail (the incumbent stays). propose() therefore
+// draws the next `width` candidates as run_single would if every one of them failed -- same generator stream, same SSC0
+// bookkeeping -- and consume() walks the costs in order: up to the first success they ARE run_single's steps; the
+// success is applied, the generator is rewound to where it stood after that candidate was drawn, and the rest of the batch
+// (drawn around the old incumbent) is dropped. The accepted sequence, every sigma and the result are those of run_single
+// evaluated one candidate at a time; only the number of evaluations spent is larger.
 void DdsSearch::propose(std::vector<std::vector<double>> &cands)
 {
   cands.clear();
-  if (!started_) {
-    cands.push_back(xb_);
-    pending_.clear();
-    if (num_threads_ > 0) {
-      // run_mt draws its first generation from the start vector, sigma_init and the evaluation counter alone
-      // (dds.cpp:66-83): none of it depends on f(xstart), which the selection only needs afterwards (dds.cpp:88-98).
-      // The start vector and the first generation therefore go out as ONE batch -- same candidates, same random draws,
-      // same selection, one launch set less per frame.
-      nfunc_ = 1;
-      const int nt = std::min(nfunc_max_ - nfunc_, num_threads_);
-      for (int i = 0; i < nt; i++) { pending_.push_back(candidate(nfunc_)); nfunc_++; }
-      cands.insert(cands.end(), pending_.begin(), pending_.end());
+  pending_.clear();
+  spec_pts_.clear();
+  if (num_threads_ <= 0) {
+    if (!started_) cands.push_back(xb_);
+    int width = 1;
+    if (spec_ > 1) {
+      // expected useful steps of a batch of w: (1 - (1-q)^w) / q; a width of about 1/q keeps two thirds of the work useful
+      width = std::clamp((int)std::lround(1.0 / std::max(q_est_, 1e-3)), 2, spec_);
+      if (!started_) width = std::max(width - 1, 1);
+    } else if (!started_) width = 0;
+    const double sigma0 = sigma_; const int ns0 = nsucc_, nf0 = nfail_, nfunc0 = nfunc_;
+    const std::mt19937 rng0 = eng_;
+    int nf = started_ ? nfunc_ : 1;
+    for (int i = 0; i < width && nf < nfunc_max_; i++) {
+      SpecPoint sp;
+      sp.sigma = sigma_; sp.nsucc = nsucc_; sp.nfail = nfail_; sp.nfunc = nf;
+      pending_.push_back(candidate(nf));
+      sp.rng_after = eng_;
+      spec_pts_.push_back(sp);
+      ssc0_step(false);                                                 // assume it fails
+      nf++;
     }
+    // the speculated bookkeeping is re-applied by consume(); restore what propose() may not change
+    sigma_ = sigma0; nsucc_ = ns0; nfail_ = nf0; nfunc_ = nfunc0;
+    if (pending_.empty()) eng_ = rng0;
+    cands.insert(cands.end(), pending_.begin(), pending_.end());
+    evaluated_ += (long long)cands.size();
     return;
   }
-  const int nt = num_threads_ <= 0 ? 1 : std::min(nfunc_max_ - nfunc_, num_threads_);
+  if (!started_) {
+    cands.push_back(xb_);
+    // run_mt draws its first generation from the start vector, sigma_init and the evaluation counter alone
+    // (dds.cpp:66-83): none of it depends on f(xstart), which the selection only needs afterwards (dds.cpp:88-98).
+    // The start vector and the first generation therefore go out as ONE batch -- same candidates, same random draws,
+    // same selection, one launch set less per frame.
+    nfunc_ = 1;
+    const int nt = std::min(nfunc_max_ - nfunc_, num_threads_);
+    for (int i = 0; i < nt; i++) { pending_.push_back(candidate(nfunc_)); nfunc_++; }
+    cands.insert(cands.end(), pending_.begin(), pending_.end());
+    evaluated_ += (long long)cands.size();
+    return;
+  }
+  const int nt = std::min(nfunc_max_ - nfunc_, num_threads_);
   for (int i = 0; i < nt; i++) { cands.push_back(candidate(nfunc_)); nfunc_++; }
   pending_ = cands;
+  evaluated_ += (long long)cands.size();
 }
 void DdsSearch::consume(const double *costs)
 {
+  if (num_threads_ <= 0) {                                              // run_single + SSC0
+    if (!started_) { fb_ = costs[0]; started_ = true; nfunc_ = 1; costs += 1; }
+    for (size_t i = 0; i < pending_.size(); i++) {
+      const SpecPoint &sp = spec_pts_[i];
+      sigma_ = sp.sigma; nsucc_ = sp.nsucc; nfail_ = sp.nfail;        // equal to the running state: kept for clarity
+      const bool ok = costs[i] < fb_;
+      if (ok) { xb_ = pending_[i]; fb_ = costs[i]; }
+      ssc0_step(ok);
+      nfunc_ = sp.nfunc + 1;
+      q_est_ = 0.95 * q_est_ + 0.05 * (ok ? 1.0 : 0.0);
+      if (ok) { eng_ = sp.rng_after; break; }                           // later candidates were drawn around the old incumbent
+    }
+    return;
+  }
   if (!started_) {
     fb_ = costs[0]; started_ = true;
-    if (num_threads_ <= 0) { nfunc_ = 1; return; }
     costs += 1;                                                        // the first generation travelled with the start vector
     if (pending_.empty()) return;
   }
   const int nt = (int)pending_.size();
-  if (num_threads_ <= 0) {                                              // run_single + SSC0 (ssc.h:6-37)
-    const bool ok = costs[0] < fb_;
-    if (ok) { xb_ = pending_[0]; fb_ = costs[0]; nsucc_ += 1; nfail_ = 0; } else { nsucc_ = 0; nfail_ += 1; }
-    if (nsucc_ >= 3) { sigma_ = sigma_ * 2.0; nsucc_ = 0; } else if (nfail_ >= 50) { sigma_ = sigma_ / 2.0; nfail_ = 0; }
-    sigma_ = std::clamp(sigma_, 0.05, 0.5);
-  } else {                                                              // run_mt + SSC1 (dds.cpp:88-98, ssc.h:40-60)
+  {                                                                     // run_mt + SSC1 (dds.cpp:88-98, ssc.h:40-60)
     const double fb_old = fb_;
     int nsucc = 0;
     for (int i = 0; i < nt; i++)
@@ -525,7 +575,7 @@ static int frames_encode_streams(Engine *e, const sac_cfg &cfg, int nch, int max
                                  const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                                  const sac_window *const *resident, const int32_t *resident_means)
 {
-  const int kMaxPar = 4;
+  const int par = std::min(std::clamp(cfg.inflight, 1, 64), nframes);   // frames in flight: one worker (host thread + helper engine) each
   const int kBase = 8;                                               // helper slots 0..3 serve final passes of the main engine
   std::vector<std::vector<uint8_t>> outs(nframes);
   std::vector<int> rcs(nframes, SAC_OK);
@@ -533,22 +583,25 @@ static int frames_encode_streams(Engine *e, const sac_cfg &cfg, int nch, int max
   std::vector<std::array<float, kProfileSize>> profs(nframes);
   sac_cfg one = cfg;
   one.frame_parallel = 0; one.reset = 1;
-  for (int i = 0; i < std::min(kMaxPar, nframes); i++) if (!e->helper(kBase + i)) return SAC_E_CUDA;
-  for (int f0 = 0; f0 < nframes; f0 += kMaxPar) {
-    const int f1 = std::min(nframes, f0 + kMaxPar);
-    std::vector<std::thread> th;
-    for (int f = f0; f < f1; f++) {
-      th.emplace_back([&, f]() {
-        Engine *h = e->helpers[kBase + (f - f0)];
-        cudaSetDevice(h->device);
+  for (int i = 0; i < par; i++) if (!e->helper(kBase + i)) return SAC_E_CUDA;
+  // workers pull the next frame as soon as they are done with one: the GPU never waits for the slowest frame of a group
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  for (int w = 0; w < par; w++) {
+    th.emplace_back([&, w]() {
+      Engine *h = e->helpers[kBase + w];
+      cudaSetDevice(h->device);
+      for (;;) {
+        const int f = next.fetch_add(1);
+        if (f >= nframes) break;
         for (int i = 0; i < kProfileSize; i++) profs[f][i] = kBaseProfile[i][2];
         rcs[f] = frames_encode_seq(h, one, nch, max_framesize, 1, planes ? planes + (size_t)f * nch : nullptr, numsamples ? numsamples + f : nullptr,
                                    profs[f].data(), outs[f], resident ? resident + f : nullptr, resident_means ? resident_means + (size_t)f * nch : nullptr);
         if (rcs[f]) errs[f] = sac_last_error();
-      });
-    }
-    for (auto &t : th) t.join();
+      }
+    });
   }
+  for (auto &t : th) t.join();
   for (int f = 0; f < nframes; f++) {
     if (rcs[f]) { set_error(errs[f]); return rcs[f]; }
     out.insert(out.end(), outs[f].begin(), outs[f].end());
@@ -755,7 +808,7 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
         for (int i = 0; i < D; i++) xs[i] = fw[f].profile[dims[i]];
         if (cfg.search == SAC_SEARCH_DE) ss.emplace_back(new DeSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.sigma));
         else if (cfg.search == SAC_SEARCH_CMA) ss.emplace_back(new CmaSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, 0.0));   // cma_cfg.sigma_init stays 0 (cmdline.cpp:232-235)
-        else ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma));
+        else ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma, cfg.spec));
         const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
         wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
       }
@@ -1188,6 +1241,27 @@ double sac_dds_run(int D, const double *xmin, const double *xmax, const double *
   return s.best_cost();
 }
 
+double sac_dds_run_spec(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init, int spec,
+                        sac_eval_fn eval, void *user, double *xbest, long long *evaluated)
+{
+  if (D <= 0 || !xmin || !xmax || !xstart || !eval || nfunc_max < 1) { set_error("sac_dds_run_spec: bad argument"); return std::numeric_limits<double>::quiet_NaN(); }
+  DdsSearch s(D, xmin, xmax, xstart, nfunc_max, 0, sigma_init, spec);
+  std::vector<std::vector<double>> cands;
+  std::vector<double> X, cost;
+  do {
+    s.propose(cands);
+    if (cands.empty()) break;
+    X.clear();
+    for (auto &c : cands) X.insert(X.end(), c.begin(), c.end());
+    cost.assign(cands.size(), 0.0);
+    if (eval(X.data(), (int)cands.size(), D, cost.data(), user)) { set_error("sac_dds_run_spec: evaluator aborted"); break; }
+    s.consume(cost.data());
+  } while (!s.done());
+  if (xbest) std::copy(s.best_x().begin(), s.best_x().end(), xbest);
+  if (evaluated) *evaluated = s.evaluated();
+  return s.best_cost();
+}
+
 double sac_de_run(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, double sigma_init, sac_eval_fn eval,
                   void *user, double *xbest)
 {
@@ -1307,6 +1381,7 @@ void sac_cfg_default(sac_cfg *c)
   c->optimize = 0; c->fraction = 0; c->maxnfunc = 0; c->num_threads = 0; c->sigma = 0.2; c->optk = 4;
   c->cost_kind = SAC_COST_ENTROPY; c->reset = 0; c->zero_mean = 1; c->sparse_pcm = 1; c->max_framelen = 20; c->adapt_block = 1;
   c->frame_parallel = 0; c->verbose = 0; c->search = SAC_SEARCH_DDS;
+  c->spec = 16; c->inflight = 4; c->grade = 0;
 }
 int sac_cfg_preset(sac_cfg *c, const char *name)                        // cmdline.cpp:127-156
 {

@@ -27,8 +27,11 @@ public:
 // DDS (OptDDS::run_single / run_mt, /root/reference src/opt/dds.cpp:33-106)
 class DdsSearch : public Search {
 public:
-  DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads, double sigma_init);
+  // spec > 1 (sequential search only, num_threads <= 0): speculative batches, see propose()
+  DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads, double sigma_init,
+            int spec = 1);
   bool done() const override { return started_ && nfunc_ >= nfunc_max_; }
+  long long evaluated() const { return evaluated_; }   // candidates handed out so far (>= nfunc() when speculating)
   void propose(std::vector<std::vector<double>> &cands) override;
   void consume(const double *costs) override;
   const std::vector<double> &best_x() const override { return xb_; }
@@ -48,6 +51,14 @@ private:
   int nsucc_ = 0, nfail_ = 0;                 // SSC0(3,50)
   double p_succ_ = 0.05;                      // SSC1(0.05,0.10,0.05)
   std::vector<std::vector<double>> pending_;
+  // speculative sequential search: state of run_single as it would be BEFORE the outcome of pending_[i] is known, under
+  // the assumption that every earlier candidate of the batch failed, and the generator state after drawing pending_[i]
+  struct SpecPoint { double sigma; int nsucc, nfail, nfunc; std::mt19937 rng_after; };
+  std::vector<SpecPoint> spec_pts_;
+  int spec_ = 1;
+  double q_est_ = 0.5;                        // running estimate of the per-step success rate (sizes the batches)
+  long long evaluated_ = 0;
+  void ssc0_step(bool ok);
 };
 
 // Differential evolution, the reference's --opt-cfg=de (OptDE, src/opt/de.cpp, de.h: JADE-style current-to-pbest/1/bin,

@@ -167,6 +167,9 @@ int main(int argc, const char *argv[])
       else if (key == "--ZERO-MEAN") cfg.zero_mean = !(val == "NO" || val == "0");
       else if (key == "--GPU") gpu = std::atoi(val.c_str());
       else if (key == "--FRAME-PARALLEL") cfg.frame_parallel = val.empty() ? 2 : std::max(0, std::min(2, std::atoi(val.c_str())));
+      else if (key == "--SPEC") cfg.spec = std::clamp(std::atoi(val.c_str()), 1, 256);          // candidates per speculative batch
+      else if (key == "--INFLIGHT") cfg.inflight = std::clamp(std::atoi(val.c_str()), 1, 64);   // frames in flight (--frame-parallel=2)
+      else if (key == "--GRADE") cfg.grade = std::clamp(std::atoi(val.c_str()), 0, 1);          // 1: search-grade kernels for the search
       else std::cerr << "warning: unknown option '" << param << "'\n";
     } else {
       if (first) { in = param; first = false; } else out = param;
@@ -178,11 +181,11 @@ int main(int argc, const char *argv[])
     std::printf("\n  Time:    [00:00:00]\n");                          // cmdline.cpp:355-356
     return rc;
   }
-  // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step, which
-  // on a GPU is one chain per launch. Unless the user says otherwise the DDS search therefore runs the reference's own
-  // population variant (OptDDS::run_mt, dds.cpp:63-106) in about 8 generations (an eighth of the evaluation budget per
-  // generation, at most 128: --best -> 125, --high -> 13); --opt-cfg=dds,0 restores the sequential search.
-  if (mode == ENCODE && cfg.optimize && cfg.search == SAC_SEARCH_DDS && !gen_given) cfg.num_threads = std::clamp((cfg.maxnfunc + 7) / 8, 1, 128);
+  // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step. It stays the
+  // default here and is evaluated in speculative batches (sac_cfg::spec, sac_dds_run_spec): same accepted sequence and
+  // result as one candidate at a time, but tens of chains per launch. --opt-cfg=dds,N (N > 0) selects the reference's
+  // population variant (OptDDS::run_mt, dds.cpp:63-106) as it does there.
+  (void)gen_given;
   // console output mirrors CmdLine::Process (cmdline.cpp:245-358): Open / PrintWav / Create / PrintMode / MD5 / ratio line
   const auto t_all = std::chrono::steady_clock::now();
   std::vector<uint8_t> img;
@@ -221,8 +224,9 @@ int main(int argc, const char *argv[])
       std::printf("  Optimize: %s %.1f%%,n=%d,%s,k=%d\n", cfg.search == SAC_SEARCH_DE ? "DE" : (cfg.search == SAC_SEARCH_CMA ? "" : "DDS"),
                   cfg.fraction * 100.0, cfg.maxnfunc, cs[cfg.cost_kind], cfg.optk);
     }
-    if (cfg.frame_parallel || (cfg.optimize && cfg.num_threads > 0))                                     // not in the reference: how the GPU is fed
-      std::printf("  B200: generation %d, frame-parallel %d, gpu %d\n", cfg.search == SAC_SEARCH_DE ? 30 : cfg.num_threads, cfg.frame_parallel, gpu);
+    if (cfg.optimize)                                                                                   // not in the reference: how the GPU is fed
+      std::printf("  B200: %s %d, frame-parallel %d (in flight %d), search grade %d, gpu %d\n", cfg.num_threads > 0 || cfg.search != SAC_SEARCH_DDS ? "generation" : "speculative batch",
+                  cfg.search == SAC_SEARCH_DE ? 30 : (cfg.search == SAC_SEARCH_CMA ? 1 : (cfg.num_threads > 0 ? cfg.num_threads : cfg.spec)), cfg.frame_parallel, cfg.inflight, cfg.grade, gpu);
     std::printf("\n");
     rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
     if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
