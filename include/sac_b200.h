@@ -29,7 +29,15 @@ extern "C" {
 #define SAC_PROFILE_SIZE 58   /* src/libsac/profile.cpp:10 */
 #define SAC_SEARCH_DIMS 56    /* all but coefficients 56,57 (src/libsac/libsac.cpp:469-475) */
 
-enum { SAC_OK = 0, SAC_E_NODEVICE = -1, SAC_E_CUDA = -2, SAC_E_ARG = -3, SAC_E_IO = -4, SAC_E_FORMAT = -5, SAC_E_UNSUPPORTED = -6 };
+enum { SAC_OK = 0, SAC_E_NODEVICE = -1, SAC_E_CUDA = -2, SAC_E_ARG = -3, SAC_E_IO = -4, SAC_E_FORMAT = -5, SAC_E_UNSUPPORTED = -6,
+       SAC_E_MD5 = -7 /* decoded audio does not hash to the MD5 in the header: no output is delivered */ };
+/* Byte 17 of the .sac header (reserved, 0 in files of the reference, src/file/sac.cpp:15-38) names the ARITHMETIC the frame
+ * payloads were predicted in: the decoder re-runs the predictor and must repeat the encoder's fp64 bit pattern (SURVEY.md
+ * fact 1). 0 = some build of the reference (libm, compiler-dependent contraction), 1 = this library's canonical arithmetic
+ * (include/sac_canon_math.h). Files written here carry 1; the reference ignores the byte. Decoding a variant-0 file is
+ * attempted (short material often agrees) and, like every decode, succeeds only if the audio MD5 matches; other values are refused. */
+#define SAC_ARITH_REFERENCE 0
+#define SAC_ARITH_CANONICAL 1
 /* FrameCoder::SearchCost (src/libsac/libsac.h:14) */
 enum { SAC_COST_L1 = 0, SAC_COST_RMS = 1, SAC_COST_ENTROPY = 2, SAC_COST_GOLOMB = 3, SAC_COST_BITPLANE = 4 };
 
@@ -49,6 +57,12 @@ long long sac_engine_launches(const sac_engine *);
  * [0] predictor (ols_kernel + cascade_kernel) [1] bitplane [2] entropy/other [3] ols_kernel alone; out_ms[4], out_launches[4] */
 void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_launches);
 
+/* device time (ms) of every population evaluation since the engine was created, by kernel class, summed over the engine and its
+ * helper engines (frames in flight): [0] OLS kernels [1] cascade kernels [2] bitplane cost kernel [3] other cost kernels. CUDA
+ * events on each engine's own stream; with several streams in flight the spans overlap, so the SHARES are meaningful, the sum
+ * exceeds the wall time. *out_calls (may be null): evaluations timed. */
+void sac_engine_total_timing(const sac_engine *, double *out_ms4, long long *out_calls);
+
 /* Exact de-duplication (on by default): chains of one call whose inputs are identical -- same planes, range, k and
  * channel parameters -- are evaluated once, and OLS stages with identical OLS parameters are computed once and shared
  * (late in a DDS search most candidates leave one channel untouched). Results are bit-identical with and without.
@@ -56,6 +70,15 @@ void sac_engine_last_timing(const sac_engine *, double *out_ms, long long *out_l
  * process start. */
 int sac_engine_set_dedup(sac_engine *, int on);
 void sac_dedup_totals(long long *out3);
+
+/* Arithmetic of sac_predict / sac_eval_population / sac_eval_jobs on this engine: 0 = canonical (default; the decoder's bits),
+ * 1 = search-grade kernels (same formulas; summation order, fused operations and schedule are free: costs equal the canonical
+ * ones except where a residual flips at a rounding boundary). sac_frames_encode sets it from sac_cfg::grade for
+ * the search and always runs the final pass canonically. Returns the previous value. flags of sac_predict: bit 0 non-finite
+ * prediction, bit 1 (search grade only) a weight met the +-10 clamp under look-ahead (sac_eval_* re-evaluate such jobs canonically).
+ * sac_engine_grade_stats: chains through the small / large search-grade cascade, the canonical fallback, jobs re-evaluated. */
+int sac_engine_set_grade(sac_engine *, int grade);
+void sac_engine_grade_stats(const sac_engine *, long long *out4);
 
 /* measured DFMA throughput of the device (GFLOP/s, 2 flop per fma; CUDA events): the fp64 roofline denominator */
 double sac_fp64_peak_gflops(sac_engine *);

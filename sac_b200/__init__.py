@@ -69,7 +69,10 @@ def lib():
         L.sac_engine_launches.restype = C.c_longlong
         L.sac_engine_launches.argtypes = [C.c_void_p]
         L.sac_engine_last_timing.argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_longlong)]
+        L.sac_engine_total_timing.argtypes = [C.c_void_p, _f64p, C.POINTER(C.c_longlong)]
         L.sac_engine_set_dedup.argtypes = [C.c_void_p, C.c_int]
+        L.sac_engine_set_grade.argtypes = [C.c_void_p, C.c_int]
+        L.sac_engine_grade_stats.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         L.sac_dedup_totals.argtypes = [C.POINTER(C.c_longlong)]
         L.sac_window_create.restype = C.c_void_p
         L.sac_window_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(_i32p), C.c_int, _i32p]
@@ -370,6 +373,21 @@ class Engine:
     def set_dedup(self, on):
         """exact de-duplication of identical chains / OLS stages within a call; returns the previous setting"""
         return int(lib().sac_engine_set_dedup(self.h, int(bool(on))))
+
+    def total_timing(self):
+        """device ms since creation by kernel class (ols, cascade, bitplane, other) over all streams + evaluations timed"""
+        ms = (C.c_double * 4)(); calls = C.c_longlong(0)
+        lib().sac_engine_total_timing(self.h, ms, C.byref(calls))
+        return list(ms), int(calls.value)
+
+    def set_grade(self, grade):
+        """0 = canonical arithmetic, 1 = search-grade kernels for predict / eval_population; returns the previous value"""
+        return int(lib().sac_engine_set_grade(self.h, int(grade)))
+
+    def grade_stats(self):
+        out = (C.c_longlong * 4)()
+        lib().sac_engine_grade_stats(self.h, out)
+        return list(out)
 
     @staticmethod
     def dedup_totals():

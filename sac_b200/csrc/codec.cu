@@ -18,6 +18,8 @@
 #include <array>
 #include <atomic>
 #include <memory>
+#include <mutex>
+#include <cstdlib>
 #include <string>
 #include <thread>
 
@@ -123,6 +125,7 @@ void DdsSearch::consume(const double *costs)
       const SpecPoint &sp = spec_pts_[i];
       sigma_ = sp.sigma; nsucc_ = sp.nsucc; nfail_ = sp.nfail;        // equal to the running state: kept for clarity
       const bool ok = costs[i] < fb_;
+      if (trace_on_) trace_.emplace_back(costs[i], pending_[i]);
       if (ok) { xb_ = pending_[i]; fb_ = costs[i]; }
       ssc0_step(ok);
       nfunc_ = sp.nfunc + 1;
@@ -627,6 +630,7 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
                              const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                              const sac_window *const *resident, const int32_t *resident_means)
 {
+  e->grade = cfg.grade ? 1 : 0;                                      // arithmetic of the search evaluations; final passes are canonical
   std::vector<FrameWork> fw(nframes);
   struct Cleanup { std::vector<FrameWork> &f; bool own; ~Cleanup() { if (own) for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw, resident == nullptr};
   // ---- analysis + upload (or windows already resident in HBM) ----
@@ -808,7 +812,11 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
         for (int i = 0; i < D; i++) xs[i] = fw[f].profile[dims[i]];
         if (cfg.search == SAC_SEARCH_DE) ss.emplace_back(new DeSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.sigma));
         else if (cfg.search == SAC_SEARCH_CMA) ss.emplace_back(new CmaSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, 0.0));   // cma_cfg.sigma_init stays 0 (cmdline.cpp:232-235)
-        else ss.emplace_back(new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma, cfg.spec));
+        else {
+          DdsSearch *ds = new DdsSearch(D, xmin.data(), xmax.data(), xs.data(), cfg.maxnfunc, cfg.num_threads, cfg.sigma, cfg.spec);
+          if (std::getenv("SACB_TRACE_DDS")) ds->trace(true);
+          ss.emplace_back(ds);
+        }
         const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
         wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
       }
@@ -840,6 +848,22 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
           off += cands[si].size();
           if (cfg.verbose > 1)
             std::fprintf(stderr, "  frame %d DDS %5d: %0.4f s=%0.3f\n", f0 + (int)si, ss[si]->nfunc(), ss[si]->best_cost(), ss[si]->sigma());
+        }
+      }
+      if (const char *tp = std::getenv("SACB_TRACE_DDS")) {           // probe: the steps of the sequential search, one line each
+        static std::mutex trace_mu;
+        std::lock_guard<std::mutex> lk(trace_mu);
+        if (FILE *tf = std::fopen(tp, "a")) {
+          for (int f = f0; f < f1; f++)
+            if (auto *ds = dynamic_cast<DdsSearch *>(ss[f - f0].get())) {
+              int step = 1;
+              for (const auto &pr : ds->traced()) {
+                std::fprintf(tf, "{\"frame_n\": %d, \"step\": %d, \"cost\": %.17g, \"x\": [", fw[f].n, step++, pr.first);
+                for (size_t i = 0; i < pr.second.size(); i++) std::fprintf(tf, "%s%.9g", i ? ", " : "", pr.second[i]);
+                std::fprintf(tf, "]}\n");
+              }
+            }
+          std::fclose(tf);
         }
       }
       for (int f = f0; f < f1; f++) {
@@ -884,6 +908,7 @@ static long long frame_decode(Engine *e, int nch, const uint8_t *in, long long l
     const uint16_t flag = get16(in + pos + 16);
     mapped[ch] = (flag >> 9) != 0;                                  // ReadBlockHeader, libsac.cpp:551-564
     maxbpn[ch] = flag & 0xff;
+    if (maxbpn[ch] > 30) { set_error("block header: bit plane count out of range"); return SAC_E_FORMAT; }   // the model has 32 planes (vle.h), as sac_bitplane_decode checks
     pos += 18;
     poff[ch] = pos;
     if (pos + plen[ch] > len) { set_error("truncated payload"); return SAC_E_FORMAT; }
@@ -1078,13 +1103,24 @@ static int container_plan(const sac_cfg &cfg, const uint8_t *wav, size_t wav_len
     set_error("unsupported input format: must be 1-16 bit, mono/stereo, pcm");          // cmdline.cpp:253-262
     return SAC_E_UNSUPPORTED;
   }
+  {
+    // the sample container must be the 1..3 bytes wav_unpack / wav_pack handle AND the width the decoder rebuilds from the
+    // bit depth alone (blockalign = nch * ceil(bits / 8), wav.cpp:126-164): 24 valid bits in a 32-bit container or a depth of
+    // 0 bits would otherwise be coded as silence under the MD5 of the real PCM. (The reference prints "error: unknown csize"
+    // for such input and writes a file that cannot be restored; here the input is refused.)
+    const int cs = wi.blockalign / wi.nch;
+    if (wi.bits < 1 || cs < 1 || cs > 3 || cs != (wi.bits + 7) / 8) {
+      set_error("unsupported input format: sample container does not match the bit depth (must be 1-16 bit, mono/stereo, pcm)");
+      return SAC_E_UNSUPPORTED;
+    }
+  }
   const int max_framesize = cp.max_framesize = cfg.max_framelen * wi.samplerate;
   if (max_framesize <= 0) { set_error("bad frame length"); return SAC_E_ARG; }
   // ---- .sac header (sac.cpp:15-38) + MD5 ----
   out.clear();
   out.push_back('S'); out.push_back('A'); out.push_back('C'); out.push_back('2');
   push16(out, (uint16_t)wi.nch); push32(out, (uint32_t)wi.samplerate); push16(out, (uint16_t)wi.bits); push32(out, wi.numsamples);
-  out.push_back((uint8_t)cfg.max_framelen); out.push_back(0);
+  out.push_back((uint8_t)cfg.max_framelen); out.push_back((uint8_t)SAC_ARITH_CANONICAL);   // byte 17: arithmetic variant (sac_b200.h)
   push32(out, wi.metadatasize());
   pack_metadata(wi, out);
   cp.md5pos = out.size();
@@ -1146,7 +1182,13 @@ static int decode_image(Engine *e, const uint8_t *sac, size_t len, std::vector<u
   wi.nch = get16(sac + 4); wi.samplerate = (int)get32(sac + 6); wi.bits = get16(sac + 10); wi.numsamples = get32(sac + 12);
   const int max_framelen = sac[16];
   const uint32_t mdsize = get32(sac + 18);
-  if (22 + (size_t)mdsize + 16 > len || wi.nch < 1 || wi.nch > 2) { set_error("corrupt .sac header"); return SAC_E_FORMAT; }
+  if (22 + (size_t)mdsize + 16 > len || wi.nch < 1 || wi.nch > 2 || wi.bits < 1 || wi.bits > 24) { set_error("corrupt .sac header"); return SAC_E_FORMAT; }
+  const int arith = sac[17];
+  if (arith != SAC_ARITH_REFERENCE && arith != SAC_ARITH_CANONICAL) { set_error("unknown arithmetic variant in the .sac header (byte 17)"); return SAC_E_UNSUPPORTED; }
+  {
+    const long long mfs = (long long)max_framelen * (long long)wi.samplerate;   // crafted headers must not overflow the frame capacity
+    if (max_framelen <= 0 || wi.samplerate <= 0 || mfs > (1LL << 28)) { set_error("corrupt .sac header: frame length out of range"); return SAC_E_FORMAT; }
+  }
   if (unpack_metadata(sac + 22, mdsize, wi)) { set_error("unpackmetadata mismatch"); return SAC_E_FORMAT; }
   size_t pos = 22 + mdsize;
   uint8_t want[16];
@@ -1193,6 +1235,14 @@ static int decode_image(Engine *e, const uint8_t *sac, size_t len, std::vector<u
     st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, dig, 16);
     st->md5_ok = std::memcmp(dig, want, 16) == 0;
     st->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (std::memcmp(dig, want, 16) != 0) {
+    // never hand out audio that is not the encoder's input (a lossless archiver must not corrupt silently)
+    set_error(arith == SAC_ARITH_REFERENCE
+                  ? "audio MD5 mismatch: the file was written by a build of the reference (arithmetic variant 0) whose fp64 predictor "
+                    "arithmetic differs from this decoder's canonical arithmetic; decode it with the build that wrote it"
+                  : "audio MD5 mismatch: the stream is damaged");
+    return SAC_E_MD5;
   }
   return SAC_OK;
 }
@@ -1485,7 +1535,7 @@ int sac_decode_memory(sac_engine *h, const uint8_t *sac, long long sac_len, uint
   if (!e || !sac || sac_len <= 0 || !out_len) { set_error("sac_decode_memory: bad argument"); return SAC_E_ARG; }
   std::vector<uint8_t> buf;
   int rc = decode_image(e, sac, (size_t)sac_len, buf, st);
-  if (rc) return rc;
+  if (rc) { *out_len = 0; return rc; }
   *out_len = (long long)buf.size();
   if (!out || (long long)buf.size() > cap) { set_error("output buffer too small"); return SAC_E_ARG; }
   std::memcpy(out, buf.data(), buf.size());

@@ -31,7 +31,10 @@ public:
   DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads, double sigma_init,
             int spec = 1);
   bool done() const override { return started_ && nfunc_ >= nfunc_max_; }
-  long long evaluated() const { return evaluated_; }   // candidates handed out so far (>= nfunc() when speculating)
+  long long evaluated() const { return evaluated_; }
+  // every step of the sequential search as (candidate, cost), in order -- recorded when trace(true) was called (probes)
+  void trace(bool on) { trace_on_ = on; }
+  const std::vector<std::pair<double, std::vector<double>>> &traced() const { return trace_; }   // candidates handed out so far (>= nfunc() when speculating)
   void propose(std::vector<std::vector<double>> &cands) override;
   void consume(const double *costs) override;
   const std::vector<double> &best_x() const override { return xb_; }
@@ -58,6 +61,8 @@ private:
   int spec_ = 1;
   double q_est_ = 0.5;                        // running estimate of the per-step success rate (sizes the batches)
   long long evaluated_ = 0;
+  bool trace_on_ = false;
+  std::vector<std::pair<double, std::vector<double>>> trace_;
   void ssc0_step(bool ok);
 };
 

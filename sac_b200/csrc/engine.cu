@@ -151,6 +151,7 @@ int Engine::init(int dev, const Engine *parent)
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once_dev[dev & 63], [] {
       attr_err = predictor_enc_init_attributes();
+      if (attr_err == cudaSuccess) attr_err = predictor_sg_init_attributes();
       if (attr_err == cudaSuccess) attr_err = predictor_init_attributes();
       if (attr_err == cudaSuccess) attr_err = bitplane_init_attributes();
     });
@@ -171,7 +172,7 @@ int Engine::init(int dev, const Engine *parent)
   if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_DEDUP")) dedup = std::atoi(s) != 0;
   if (parent) {
-    dedup = parent->dedup;
+    dedup = parent->dedup; grade = parent->grade;
     enc_smem_bytes = parent->enc_smem_bytes; ols_smem_bytes = parent->ols_smem_bytes; ols_smem_cap_bytes = parent->ols_smem_cap_bytes; smem_bytes = parent->smem_bytes;
     bt = parent->bt;                                                 // shared device tables (owned by the parent)
     return SAC_OK;
@@ -186,6 +187,7 @@ void Engine::destroy()
   helpers.clear();
   if (stream) cudaStreamSynchronize(stream);
   d_descs.release(); h_descs.release(); d_scratch.release(); d_scratch_ols.release(); d_plpc.release(); d_resid.release(); d_sums.release(); d_flags.release();
+  d_idx.release(); h_idx.release();
   h_sums.release(); h_flags.release(); d_bpjobs.release(); h_bpjobs.release(); d_csig0.release(); d_hist.release();
   d_cost.release(); h_cost.release(); d_bytes.release(); h_stage.release(); d_sparse.release(); h_sparse.release();
   if (!is_helper) bt.destroy();
@@ -210,7 +212,7 @@ void Engine::begin_call()
 // parameters -- or at least its 8 OLS parameters -- untouched: those chains (resp. their OLS stage) coincide.
 //   slot_of[c]  unique chain ("slot") of logical chain c = (job, coded channel); residuals, sums, flags are per slot
 //   OLS stage   one ols_kernel CTA per distinct (planes, range, k, OLS parameters); slots share its p_lpc plane
-int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride)
+int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride, int grade_req)
 {
   SACB_CUDA(cudaSetDevice(device));
   chain_job.clear(); chain_ch.clear();
@@ -316,9 +318,53 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   }
   SACB_CUDA(cudaMemcpyAsync(d_descs.p, h_descs.p, sizeof(ChainDesc) * (nu + nv), cudaMemcpyHostToDevice, stream));
   SACB_CUDA(cudaEventRecord(ev[0], stream));
-  SACB_CUDA(launch_predictor_enc(d_descs.p + nu, nv, d_descs.p, nu, casc_smem, ols_smem, stream, ev[4]));
-  SACB_CUDA(cudaEventRecord(ev[1], stream));
-  launches += 2; last_launches[0] += 2;                             // ols_kernel + cascade_kernel
+  ev4_recorded = true;
+  if (grade_req == 0) {
+    SACB_CUDA(launch_predictor_enc(d_descs.p + nu, nv, d_descs.p, nu, casc_smem, ols_smem, stream, ev[4]));
+    SACB_CUDA(cudaEventRecord(ev[1], stream));
+    launches += 2; last_launches[0] += 2;                           // ols_kernel + cascade_kernel
+    return SAC_OK;
+  }
+  // ---- search-grade kernels: OLS stages by matrix size class, cascades by what fits registers / shared memory ----
+  {
+    std::vector<int> ols_cls[3], casc[3];                           // OLS: 3 / 5 / 7 blocks; cascade: small, large, canonical fallback
+    size_t ols_sm[3] = {0, 0, 0}, casc_sm[3] = {0, 0, 0};
+    for (int v = 0; v < nv; v++) {
+      const int u = ols_rep[v];
+      const int n = ols_order(hps[slot_job[u]], slot_cc[u]);
+      const int c = ols_sg_class(n) == 3 ? 0 : (ols_sg_class(n) == 5 ? 1 : 2);
+      ols_cls[c].push_back(nu + v);
+      ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
+    }
+    const size_t kSmallCap = 112 * 1024, kLargeCap = 226 * 1024;     // two CTAs per SM / one
+    for (int u = 0; u < nu; u++) {
+      const int *vn = hps[slot_job[u]].vn[slot_cc[u]];
+      const size_t ss = cascade_sg_smem_bytes(vn, 0), sl = cascade_sg_smem_bytes(vn, 1);
+      int c = 2;
+      if (ss && ss <= kSmallCap) c = 0; else if (sl && sl <= kLargeCap) c = 1;
+      casc[c].push_back(u);
+      casc_sm[c] = std::max(casc_sm[c], c == 0 ? ss : (c == 1 ? sl : predictor_enc_shared_bytes() + (size_t)predictor_enc_smem_doubles(vn) * 8 + 64));
+    }
+    casc_sm[2] = std::min(casc_sm[2], (size_t)enc_smem_bytes);
+    sg_stats[0] += (long long)casc[0].size(); sg_stats[1] += (long long)casc[1].size(); sg_stats[2] += (long long)casc[2].size();
+    SACB_CUDA(h_idx.reserve((size_t)nu + nv));
+    SACB_CUDA(d_idx.reserve((size_t)nu + nv));
+    size_t off = 0, ooff[3], coff[3];
+    for (int c = 0; c < 3; c++) { ooff[c] = off; for (int x : ols_cls[c]) h_idx.p[off++] = x; }
+    for (int c = 0; c < 3; c++) { coff[c] = off; for (int x : casc[c]) h_idx.p[off++] = x; }
+    SACB_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.p, sizeof(int) * off, cudaMemcpyHostToDevice, stream));
+    const int cls_nb[3] = {3, 5, 7};
+    for (int c = 2; c >= 0; c--)                                    // the longest-running class first
+      if (!ols_cls[c].empty()) {
+        SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_nb[c], (int)ols_sm[c], stream));
+        launches++; last_launches[0]++;
+      }
+    SACB_CUDA(cudaEventRecord(ev[4], stream));
+    if (!casc[2].empty()) { SACB_CUDA(launch_cascade_canonical(d_descs.p, d_idx.p + coff[2], (int)casc[2].size(), (int)casc_sm[2], stream)); launches++; last_launches[0]++; }
+    if (!casc[1].empty()) { SACB_CUDA(launch_cascade_sg(d_descs.p, d_idx.p + coff[1], (int)casc[1].size(), 1, (int)casc_sm[1], stream)); launches++; last_launches[0]++; }
+    if (!casc[0].empty()) { SACB_CUDA(launch_cascade_sg(d_descs.p, d_idx.p + coff[0], (int)casc[0].size(), 0, (int)casc_sm[0], stream)); launches++; last_launches[0]++; }
+    SACB_CUDA(cudaEventRecord(ev[1], stream));
+  }
   return SAC_OK;
 }
 
@@ -361,7 +407,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(cudaEventRecord(ev[3], stream));
     SACB_CUDA(wait());
-    for (int c = 0; c < nchains; c++) ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : h_cost.p[c];
+    for (int c = 0; c < nchains; c++) ccost[c] = (h_flags.p[c] & 1) ? std::numeric_limits<double>::infinity() : h_cost.p[c];
     float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[2] += ms;
   } else if (cost_kind == SAC_COST_BITPLANE) {
     SACB_CUDA(h_bpjobs.reserve(nchains));
@@ -381,7 +427,7 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     SACB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int) * nchains, cudaMemcpyDeviceToHost, stream));
     SACB_CUDA(wait());
     for (int c = 0; c < nchains; c++)
-      ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : (double)h_sums.p[2 * nchains + c];
+      ccost[c] = (h_flags.p[c] & 1) ? std::numeric_limits<double>::infinity() : (double)h_sums.p[2 * nchains + c];
     float ms = 0; cudaEventElapsedTime(&ms, ev[2], ev[3]); last_ms[1] += ms;
   } else if (cost_kind == SAC_COST_L1 || cost_kind == SAC_COST_RMS) {
     SACB_CUDA(cudaMemcpyAsync(h_sums.p, d_sums.p, sizeof(long long) * 3 * nchains, cudaMemcpyDeviceToHost, stream));
@@ -390,13 +436,26 @@ int Engine::run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vec
     for (int c = 0; c < nchains; c++) {
       const double n = (double)rep_job(c).n;
       double v = cost_kind == SAC_COST_L1 ? h_sums.p[c] / n : std::sqrt(h_sums.p[nchains + c] / n);   // cost.h:15-41
-      ccost[c] = h_flags.p[c] ? std::numeric_limits<double>::infinity() : v;
+      ccost[c] = (h_flags.p[c] & 1) ? std::numeric_limits<double>::infinity() : v;
     }
   } else { set_error("unknown cost kind"); return SAC_E_ARG; }
-  { float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms; cudaEventElapsedTime(&ms, ev[0], ev[4]); last_ms[3] += ms; last_launches[3]++; }
+  {
+    float ms = 0, ms_ols = 0;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); last_ms[0] += ms;
+    if (ev4_recorded) { cudaEventElapsedTime(&ms_ols, ev[0], ev[4]); last_ms[3] += ms_ols; last_launches[3]++; }
+    ev4_recorded = false;
+    (void)cudaGetLastError();                                       // an optional timing query must not leave an error pending
+    total_ms[0] += ms_ols; total_ms[1] += ms - ms_ols; total_calls++;
+    if (cost_kind == SAC_COST_BITPLANE) { float b = 0; cudaEventElapsedTime(&b, ev[2], ev[3]); total_ms[2] += b; }
+    else if (cost_kind == SAC_COST_ENTROPY || cost_kind == SAC_COST_GOLOMB) { float b = 0; cudaEventElapsedTime(&b, ev[2], ev[3]); total_ms[3] += b; }
+  }
   for (size_t j = 0; j < jobs.size(); j++) cost[j] = 0.0;
+  job_inexact.assign(jobs.size(), 0);
   // sum over channels (FrameCoder::GetCost, libsac.cpp:358-361; a two-term sum is order-independent)
-  for (int c = 0; c < nlog; c++) cost[chain_job[c]] += ccost[slot_of[c]];
+  for (int c = 0; c < nlog; c++) {
+    cost[chain_job[c]] += ccost[slot_of[c]];
+    if (h_flags.p[slot_of[c]] & 2) job_inexact[chain_job[c]] = 1;   // search-grade cascade: look-ahead met the weight clamp
+  }
   return SAC_OK;
 }
 
@@ -434,6 +493,36 @@ void sac_engine_last_timing(const sac_engine *h, double *out_ms, long long *out_
 {
   const Engine *e = reinterpret_cast<const Engine *>(h);
   for (int i = 0; i < 4; i++) { if (out_ms) out_ms[i] = e->last_ms[i]; if (out_launches) out_launches[i] = e->last_launches[i]; }
+}
+
+void sac_engine_total_timing(const sac_engine *h, double *out_ms4, long long *out_calls)
+{
+  const Engine *e = reinterpret_cast<const Engine *>(h);
+  for (int i = 0; i < 4; i++) out_ms4[i] = e->total_ms[i];
+  long long calls = e->total_calls;
+  for (const Engine *x : e->helpers) {
+    double t[4]; long long c = 0;
+    sac_engine_total_timing(reinterpret_cast<const sac_engine *>(x), t, &c);
+    for (int i = 0; i < 4; i++) out_ms4[i] += t[i];
+    calls += c;
+  }
+  if (out_calls) *out_calls = calls;
+}
+
+int sac_engine_set_grade(sac_engine *h, int grade)
+{
+  Engine *e = reinterpret_cast<Engine *>(h);
+  if (!e) return -1;
+  const int prev = e->grade;
+  e->grade = grade ? 1 : 0;
+  for (Engine *x : e->helpers) sac_engine_set_grade(reinterpret_cast<sac_engine *>(x), grade);
+  return prev;
+}
+void sac_engine_grade_stats(const sac_engine *h, long long *out4)
+{
+  const Engine *e = reinterpret_cast<const Engine *>(h);
+  for (int i = 0; i < 4; i++) out4[i] = e->sg_stats[i];
+  for (const Engine *x : e->helpers) { long long t[4]; sac_engine_grade_stats(reinterpret_cast<const sac_engine *>(x), t); for (int i = 0; i < 4; i++) out4[i] += t[i]; }
 }
 
 int sac_engine_set_dedup(sac_engine *h, int on)
@@ -490,7 +579,7 @@ sac_window *sac_window_create(sac_engine *h, int nch, const int32_t *const *plan
   if (!e || nch < 1 || nch > 2 || numsamples <= 0 || !planes || !minmax) { set_error("sac_window_create: bad argument"); return nullptr; }
   cudaSetDevice(e->device);
   Window *w = new Window();
-  w->eng = e; w->nch = nch; w->numsamples = numsamples;
+  w->eng = e; w->device = e->device; w->nch = nch; w->numsamples = numsamples;
   w->d_planes[0] = w->d_planes[1] = nullptr;
   for (int i = 0; i < 2 * nch; i++) w->minmax[i] = minmax[i];
   if (nch == 1) { w->minmax[2] = minmax[0]; w->minmax[3] = minmax[1]; }
@@ -507,7 +596,7 @@ void sac_window_destroy(sac_window *h)
 {
   Window *w = reinterpret_cast<Window *>(h);
   if (!w) return;
-  cudaSetDevice(w->eng->device);
+  cudaSetDevice(w->device);
   for (int ch = 0; ch < 2; ch++) if (w->d_planes[ch]) cudaFree(w->d_planes[ch]);
   delete w;
 }
@@ -525,7 +614,7 @@ int sac_predict(sac_engine *h, const sac_window *wh, const float *profiles, int 
   }
   std::vector<int> cj, cc;
   size_t stride;
-  int rc = e->run_predict(jobs, cj, cc, stride);
+  int rc = e->run_predict(jobs, cj, cc, stride, e->grade);
   if (rc) return rc;
   const int nchains = (int)cj.size();
   SACB_CUDA(e->h_flags.reserve((size_t)2 * nchains));
@@ -594,12 +683,28 @@ int sac_eval_jobs(sac_engine *h, int njobs, const sac_window *const *wins, const
   }
   std::vector<int> cj, cc;
   size_t stride;
-  int rc = e->run_predict(jobs, cj, cc, stride);
+  int rc = e->run_predict(jobs, cj, cc, stride, e->grade);
   if (rc) return rc;
-  if (order.empty()) return e->run_cost(cost_kind, jobs, cj, cc, stride, cost);
-  rc = e->run_cost(cost_kind, jobs, cj, cc, stride, cost_sorted.data());
+  double *cdst = order.empty() ? cost : cost_sorted.data();
+  rc = e->run_cost(cost_kind, jobs, cj, cc, stride, cdst);
   if (rc) return rc;
-  for (int i = 0; i < njobs; i++) cost[order[i]] = cost_sorted[i];
+  if (e->grade) {
+    // chains whose look-ahead met the +-10 weight clamp are not search-grade exact: those jobs go through the canonical kernels
+    std::vector<int> redo;
+    for (int j = 0; j < njobs; j++) if (e->job_inexact[j]) redo.push_back(j);
+    if (!redo.empty()) {
+      e->sg_stats[3] += (long long)redo.size();
+      std::vector<Job> rj;
+      for (int j : redo) rj.push_back(jobs[j]);
+      std::vector<double> rcost(redo.size());
+      rc = e->run_predict(rj, cj, cc, stride, 0);
+      if (rc) return rc;
+      rc = e->run_cost(cost_kind, rj, cj, cc, stride, rcost.data());
+      if (rc) return rc;
+      for (size_t i = 0; i < redo.size(); i++) cdst[redo[i]] = rcost[i];
+    }
+  }
+  if (!order.empty()) for (int i = 0; i < njobs; i++) cost[order[i]] = cost_sorted[i];
   return SAC_OK;
 }
 
@@ -643,7 +748,7 @@ int sac_cost(sac_engine *h, int cost_kind, const int32_t *bufs, int count, int n
   e->begin_call();
   SACB_CUDA(cudaSetDevice(e->device));
   // one mono pseudo-window so that run_cost's bookkeeping applies; residuals are uploaded in place of predictor output
-  Window w; w.eng = e; w.nch = 1; w.numsamples = n; w.d_planes[0] = w.d_planes[1] = nullptr;
+  Window w; w.eng = e; w.device = e->device; w.nch = 1; w.numsamples = n; w.d_planes[0] = w.d_planes[1] = nullptr;
   int32_t mn = 0, mx = 0;
   for (size_t i = 0; i < (size_t)count * n; i++) { mn = std::min(mn, bufs[i]); mx = std::max(mx, bufs[i]); }
   const int32_t R = std::max(-(long long)mn, (long long)mx) > 0 ? (int32_t)std::max(-(long long)mn, (long long)mx) : 1;

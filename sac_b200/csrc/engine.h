@@ -53,6 +53,7 @@ template <class T> struct PinBuf {
 
 struct Window {           // sac_window
   struct Engine *eng;
+  int device;             // kept here: the window may outlive its engine
   int nch, numsamples;
   int32_t minmax[4];
   int32_t *d_planes[2];   // HBM, mean-free
@@ -76,6 +77,9 @@ struct Engine {           // sac_engine
   int ols_smem_cap_bytes = 100 * 1024; // OLS kernel: above this the covariance goes to HBM scratch, the work matrix stays
   long long launches = 0;
   double last_ms[4] = {0, 0, 0, 0};          // predictor (ols + cascade), bitplane, other cost kernels, ols alone
+  double total_ms[4] = {0, 0, 0, 0};         // since creation, CUDA events on this engine's stream: ols, cascade, bitplane, other cost kernels
+  long long total_calls = 0;                 // population evaluations timed into total_ms
+  bool ev4_recorded = false;                 // ev[4] (between OLS and cascade) belongs to the call being timed
   long long last_launches[4] = {0, 0, 0, 0};
 
   DevBuf<ChainDesc> d_descs;
@@ -111,6 +115,14 @@ struct Engine {           // sac_engine
   cudaEvent_t ev_wait = nullptr;
   cudaError_t wait();
 
+  // arithmetic of population evaluations (sac_cfg::grade): 1 = search-grade kernels (predictor_sg.cu); final passes and the
+  // decoder always use the canonical kernels
+  int grade = 0;
+  DevBuf<int> d_idx;              // descriptor indices per kernel class (search-grade launches)
+  PinBuf<int> h_idx;
+  std::vector<char> job_inexact;  // per job of the last run_cost: a chain hit the weight clamp under look-ahead (re-evaluate canonically)
+  long long sg_stats[4] = {0, 0, 0, 0};   // chains through cascade_sg small / large / canonical fallback, jobs re-evaluated after a clamp
+
   // chain de-duplication of the last run_predict (see engine.cu): logical chain -> slot, slot -> a representative
   bool dedup = true;
   std::vector<int> slot_of, slot_rep;
@@ -120,7 +132,7 @@ struct Engine {           // sac_engine
   int init(int dev, const Engine *parent = nullptr);
   void destroy();
   // residuals of every chain of `jobs` into d_resid (layout: chain c at c*stride); returns 0
-  int run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride);
+  int run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_job, std::vector<int> &chain_ch, size_t &stride, int grade = 0);
   // per-job cost (sum over channels) for residuals left by run_predict
   int run_cost(int cost_kind, const std::vector<Job> &jobs, const std::vector<int> &chain_job, const std::vector<int> &chain_ch,
                size_t stride, double *cost);
@@ -136,6 +148,14 @@ long long predictor_ols_scratch_doubles(int n_ols);
 size_t predictor_ols_shared_bytes();
 long long predictor_enc_smem_doubles(const int *vn);
 cudaError_t predictor_enc_init_attributes();
+cudaError_t launch_cascade_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream);
+// search-grade kernels (predictor_sg.cu)
+cudaError_t predictor_sg_init_attributes();
+size_t cascade_sg_smem_bytes(const int *vn, int large);          // 0: the chain does not fit that variant
+int ols_sg_class(int n_ols);                                     // 3, 5 or 7 (16-wide blocks per matrix dimension)
+size_t ols_sg_smem_bytes(int n_ols);
+cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_cascade_sg(const ChainDesc *d_descs, const int *d_idx, int count, int large, int smem_bytes, cudaStream_t stream);
 cudaError_t predictor_init_attributes();
 size_t predictor_enc_shared_bytes();
 cudaError_t launch_entropy(const int32_t *resid, size_t stride, const int *ns, const int *ranges, int nchains, unsigned int *hist,

@@ -901,10 +901,10 @@ __global__ void __launch_bounds__(kTeam, 5) ols_kernel(const ChainDesc *__restri
   ols_team(S, d, tid);
 }
 
-__global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc *__restrict__ descs)
+__global__ void __launch_bounds__(kEncThreads, 2) cascade_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ChainDesc &d = descs[blockIdx.x];
+  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
   EncShared &S = *reinterpret_cast<EncShared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -1024,7 +1024,14 @@ cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const C
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess) return e;
-  cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs);
+  cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs, nullptr);
+  return cudaGetLastError();
+}
+// the cascade alone over a subset of the descriptors (chains the search-grade kernels do not take)
+cudaError_t launch_cascade_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream)
+{
+  if (count <= 0) return cudaSuccess;
+  cascade_kernel<<<count, kEncThreads, smem_bytes, stream>>>(d_descs, d_idx);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,830 @@
+// predictor_sg.cu -- SEARCH-GRADE encode-direction predictor kernels (sm_100a).
+//
+// The DDS search only ranks candidates: its <= 1000 objective evaluations per frame need the reference's
+// formulas, not the decoder's bit pattern. These kernels evaluate exactly the recurrences of predictor_enc.cu (the reference's
+// Predictor, /root/reference src/libsac/pred.cpp:4-45, src/pred/{ols.cpp,ls.h,cascade.h,blend.h,rls.cpp,bias.h}) but are free
+// in summation order, fused multiply-adds, reciprocals instead of divisions -- and, above all, in SCHEDULE:
+//
+//  cascade_sg_kernel  look-ahead NLMS. With h(t) the stage history and w(t) its weights, the prediction of the NEXT sample is
+//        p(t+1) = bp(t) w0(t+1) + sum_{j>=1} h_{j-1}(t) w_j(t) + g(t) * sum_{j>=1} mu_j h_{j-1}(t) h_j(t)
+//        (w_j(t+1) = w_j(t) + mu_j g(t) h_j(t), ls.h:45-56, as long as no weight hits the +-10 clamp), and the normaliser
+//        spow(t+1) = pw_0 bp(t)^2 + sum_{j>=1} pw_j h_{j-1}(t)^2. All three sums depend on history and weights that are known
+//        BEFORE the scalar stage of sample t has produced g(t) and bp(t): the tap warps compute them (and apply the weight
+//        update of sample t-1) WHILE the scalar warps work on sample t. The serial loop dot -> reduce -> scalars -> update of
+//        predictor_enc.cu (8 450 clk/sample, 70 % of it synchronisation) becomes two concurrent streams that meet at ONE
+//        CTA barrier per sample. A clamp event (rare; counted) makes the look-ahead inexact: the chain is flagged and the
+//        engine re-evaluates it with the canonical kernel.
+//        8 tap warps (taps j >= 1 in per-thread contiguous blocks of odd length, weights in registers, tables and history in
+//        shared memory) + S (stage predictions, mix, targets, gradients; owns tap 0) + M (mix update) + R (RLS stage, its
+//        matrix-vector part computed ahead of the sample) + B (bias stage, residual, trails by one sample).
+//  ols_sg_kernel<NB>  256 threads per chain. Covariance and work matrix live in REGISTERS, lower triangle, 16 x 16 block-cyclic
+//        over the thread grid (element (i,c) on thread (i mod 16, c mod 16)); the k rank-1 updates of a block are one fused
+//        rank-k update (on the DMMA-shaped Gram product see DESIGN.md); right-looking LDL^T exchanges one column per step
+//        through a double-buffered shared-memory vector (one barrier per column, ~25 instructions per thread and column
+//        instead of ~300); L goes to shared memory packed by rows for the back substitution on warp 0.
+//
+// Results equal the canonical kernels' up to rounding: residuals differ in isolated samples where a prediction lies within
+// ~1e-12 of a rounding boundary. tests/test_gpu_grade.py states and checks the tolerance (costs, ranking).
+#include "chain.h"
+#include "sac_canon_math.h"
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <cstddef>
+#include <cstdio>
+
+namespace sacb {
+
+using sac_canon::c_exp;
+using sac_canon::c_pow;
+using sac_canon::c_round;
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSgMaxTapWarps = 8;
+enum { kBarPhase = 3, kBarS2MR = 1, kBarMR2S = 2 };                 // barrier 0 stays with __syncthreads()
+
+__device__ __forceinline__ void bar_sync(int id, int cnt) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int cnt) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(kFull, v, m); }
+__device__ __forceinline__ double shfl_idx(double v, int l) { return __shfl_sync(kFull, v, l); }
+__device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
+__device__ __forceinline__ double ldd_vol(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+
+// 1/x for normal x > 0: hardware seed (>= 20 bits) + two Newton steps
+__device__ __forceinline__ double rcp_fast(double x)
+{
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+__device__ __forceinline__ double butterfly(double v)
+{
+  v += shfl_xor(v, 16); v += shfl_xor(v, 8); v += shfl_xor(v, 4); v += shfl_xor(v, 2); v += shfl_xor(v, 1);
+  return v;
+}
+
+// =====================================================================================================================
+// cascade
+// =====================================================================================================================
+struct SgShared {
+  double sums[2][kSgMaxTapWarps][12];    // [t&1][tap warp][3*stage + {B', A', P'}]: look-ahead sums made during sample t
+  double g[2][kStages];                  // g_i(t) at [t&1]
+  double pxq[2];                         // p_lpc + p_lms of sample t at [t&1] (for B)
+  // S -> M, R (same sample)
+  double mx_p[kMixN], mx_ep[2], mx_target, bp4;
+  // M -> S
+  double v[2][kMixN], eg[2][kMixN], sw[2], rsum[2];
+  // R -> S
+  double p_rls;
+  // B state (bias.h)
+  double hist_in[8], hist_d[8], mixw[4][3], cnt[3][64], cval[3][64], bmean, bvar;
+  // layout
+  double *h[kStages], *mu[kStages], *pw[kStages], *wt[kStages];
+  int L[kStages];
+  double sum_pow[kStages];
+  int clamped, bad;
+};
+
+// TW tap warps + 4 scalar warps; R0..R3 register-resident weights per tap thread and stage
+template <int TW, int R0, int R1, int R2, int R3> struct SgCfg {
+  static constexpr int tw = TW, tap_threads = 32 * TW, threads = 32 * TW + 128, phase = 32 * TW + 64;
+  static constexpr int r0 = R0, r1 = R1, r2 = R2, r3 = R3;
+};
+using SgSmall = SgCfg<4, 15, 7, 3, 1>;     // 256 threads, 2 CTAs per SM: stages up to 1921 / 897 / 385 / 129 taps (default profile: 1280/256/32/4)
+using SgLarge = SgCfg<8, 21, 9, 5, 3>;     // 384 threads, 1 CTA per SM: anything whose tables fit shared memory (longer blocks spill weights to it)
+
+// shared-memory accesses by 32-bit address + immediate offset: one base register per array instead of one 64-bit generic
+// address per slot (ptxas otherwise hoists ~100 loop-invariant addresses out of the sample loop: 224 registers)
+template <int OFF> __device__ __forceinline__ double lds_o(uint32_t a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ double lds_a(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_a(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ double clamp10_flag(double wn, bool &clamped)
+{
+  const bool c = fabs(wn) > 10.0;
+  clamped |= c;
+  return c ? (wn > 0.0 ? 10.0 : -10.0) : wn;
+}
+
+// one register slot of a tap thread: weight update of the previous sample, then the three look-ahead sums.
+// ah -> h_{j0}(t), amu -> mu[j0], apw -> pw[j0]; slot Q is tap j0 + Q: h_{j+1}(t) = h_j(t-1) feeds the update.
+template <int R, int Q> struct TapSlots {
+  static __device__ __forceinline__ void run(double (&w)[R], uint32_t ah, uint32_t amu, uint32_t apw, int cnt, double gprev, double &hm, double &hc,
+                                             double &aB, double &aA, double &aP, bool &clamped)
+  {
+    if constexpr (Q < R) {
+      if (Q < cnt) {
+        const double hp = lds_o<8 * (Q + 1)>(ah);
+        const double m = lds_o<8 * Q>(amu);
+        const double wn = clamp10_flag(fma(m * gprev, hp, w[Q]), clamped);
+        w[Q] = wn;
+        aB = fma(hm, wn, aB);
+        aA = fma(m * hc, hm, aA);
+        aP = fma(lds_o<8 * Q>(apw), hm * hm, aP);
+        hm = hc; hc = hp;
+      }
+      TapSlots<R, Q + 1>::run(w, ah, amu, apw, cnt, gprev, hm, hc, aB, aA, aP, clamped);
+    }
+  }
+};
+
+// one stage of one tap thread for one sample. hw = shared address of h_0(t) (window start), tables at amu0 / apw0 / awt0
+// (index 0); taps j0 .. jn-1 of this thread, the first R of them with register-resident weights.
+template <int R>
+__device__ __forceinline__ void tap_stage(double (&w)[R], uint32_t hw, uint32_t amu0, uint32_t apw0, uint32_t awt0, int j0, int cnt, double gprev,
+                                          double &aB, double &aA, double &aP, bool &clamped)
+{
+  if (cnt <= 0) return;
+  const uint32_t ah = hw + 8u * (uint32_t)j0, amu = amu0 + 8u * (uint32_t)j0, apw = apw0 + 8u * (uint32_t)j0;
+  double hm = lds_o<-8>(ah), hc = lds_o<0>(ah);
+  TapSlots<R, 0>::run(w, ah, amu, apw, cnt, gprev, hm, hc, aB, aA, aP, clamped);
+  for (int q = R; q < cnt; q++) {                                   // block longer than the register slots: weights in shared memory
+    const uint32_t o = 8u * (uint32_t)q;
+    const double hp = lds_a(ah + o + 8u);
+    const double m = lds_a(amu + o);
+    const uint32_t aw = awt0 + 8u * (uint32_t)j0 + o;
+    const double wn = clamp10_flag(fma(m * gprev, hp, lds_a(aw)), clamped);
+    sts_a(aw, wn);
+    aB = fma(hm, wn, aB);
+    aA = fma(m * hc, hm, aA);
+    aP = fma(lds_a(apw + o), hm * hm, aP);
+    hm = hc; hc = hp;
+  }
+}
+
+template <class CFG>
+__device__ __forceinline__ void sg_tap_warps(SgShared &S, const ChainDesc &d, int tid)
+{
+  const int lane = tid & 31, tw = tid >> 5;
+  const int n = d.n;
+  int M[kStages], j0[kStages], cnt[kStages], pos[kStages];
+  uint32_t ah[kStages], amu[kStages], apw[kStages], awt[kStages];
+#pragma unroll
+  for (int s = 0; s < kStages; s++) {
+    const int N = d.vn[s], L = S.L[s];
+    M[s] = N + 2;
+    j0[s] = 1 + tid * L;
+    cnt[s] = min(j0[s] + L, N) - j0[s];                             // <= 0: no taps of this stage on this thread
+    pos[s] = 0;                                                      // ring position of h_0(t)
+    ah[s] = smem_u32(S.h[s]); amu[s] = smem_u32(S.mu[s]); apw[s] = smem_u32(S.pw[s]); awt[s] = S.wt[s] ? smem_u32(S.wt[s]) : 0u;
+  }
+  double w0[CFG::r0], w1[CFG::r1], w2[CFG::r2], w3[CFG::r3];
+#pragma unroll
+  for (int q = 0; q < CFG::r0; q++) w0[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < CFG::r1; q++) w1[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < CFG::r2; q++) w2[q] = 0.0;
+#pragma unroll
+  for (int q = 0; q < CFG::r3; q++) w3[q] = 0.0;
+  bool clamped = false;
+  for (int t = 0; t <= n; t++) {
+    if (t < n) {
+      const double *gp = S.g[(t + 1) & 1];                           // g(t-1)
+      const double g0 = ldd_vol(gp), g1 = ldd_vol(gp + 1), g2 = ldd_vol(gp + 2), g3 = ldd_vol(gp + 3);
+      double acc[12];
+#pragma unroll
+      for (int q = 0; q < 12; q++) acc[q] = 0.0;
+      tap_stage<CFG::r0>(w0, ah[0] + 8u * (uint32_t)pos[0], amu[0], apw[0], awt[0], j0[0], cnt[0], g0, acc[0], acc[1], acc[2], clamped);
+      tap_stage<CFG::r1>(w1, ah[1] + 8u * (uint32_t)pos[1], amu[1], apw[1], awt[1], j0[1], cnt[1], g1, acc[3], acc[4], acc[5], clamped);
+      tap_stage<CFG::r2>(w2, ah[2] + 8u * (uint32_t)pos[2], amu[2], apw[2], awt[2], j0[2], cnt[2], g2, acc[6], acc[7], acc[8], clamped);
+      tap_stage<CFG::r3>(w3, ah[3] + 8u * (uint32_t)pos[3], amu[3], apw[3], awt[3], j0[3], cnt[3], g3, acc[9], acc[10], acc[11], clamped);
+      // twelve butterflies in one: at each of the first four levels a lane keeps half of its (padded to 16) values and
+      // trades the other half with its partner; value q ends up in the lane pair whose bits 4..1 spell q
+      {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+        double a8[8], a4[4], a2[2], a1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double lo = acc[k], hi = k + 8 < 12 ? acc[k + 8] : 0.0;
+          a8[k] = (b4 ? hi : lo) + shfl_xor(b4 ? lo : hi, 16);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) a4[k] = (b3 ? a8[4 + k] : a8[k]) + shfl_xor(b3 ? a8[k] : a8[4 + k], 8);
+#pragma unroll
+        for (int k = 0; k < 2; k++) a2[k] = (b2 ? a4[2 + k] : a4[k]) + shfl_xor(b2 ? a4[k] : a4[2 + k], 4);
+        a1 = (b1 ? a2[1] : a2[0]) + shfl_xor(b1 ? a2[0] : a2[1], 2);
+        a1 = a1 + shfl_xor(a1, 1);
+        const int slot = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+        if ((lane & 1) == 0 && slot < 12) S.sums[t & 1][tw][slot] = a1;
+      }
+#pragma unroll
+      for (int s = 0; s < kStages; s++) pos[s] = pos[s] == 0 ? M[s] - 1 : pos[s] - 1;   // S pushes bp(t) at this slot during the same phase
+    }
+    bar_sync(kBarPhase, CFG::phase);
+  }
+  if (__any_sync(kFull, clamped) && lane == 0) atomicOr(&S.clamped, 1);
+}
+
+// S: stage predictions from the look-ahead sums, 2-expert mix, stage targets, gradients, history push (cascade.h:91-118)
+template <class CFG>
+__device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n;
+  const double alpha = d.proj_alpha, one_m_alpha = 1.0 - d.proj_alpha;
+  const int li = lane & 3;                                           // lanes >= 4 shadow lanes 0..3 (results unused)
+  const bool own = lane < kStages;
+  const int myM = d.vn[li] + 2;
+  double *myh = S.h[li];
+  const double my_mu = d.vmu[li], my_sp = S.sum_pow[li];
+  int pos = 0;
+  double w0 = 0.0, bp1 = 0.0, bp2 = 0.0, gprev = 0.0;                // tap 0 of stage li, bp(t-1), bp(t-2), g(t-1)
+  bool bad = false;
+  const double *plpc = d.plpc;
+  int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
+  int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
+  double lcur = lane < n ? __ldg(plpc + lane) : 0.0;
+  double lnext = 32 + lane < n ? __ldg(plpc + 32 + lane) : 0.0;
+  for (int t = 0; t <= n; t++) {
+    if (t < n) {
+      if ((t & 31) == 0 && t) {
+        vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0;
+        lcur = lnext; lnext = t + 32 + lane < n ? __ldg(plpc + t + 32 + lane) : 0.0;
+      }
+      const double val = (double)__shfl_sync(kFull, vcur, t & 31);
+      const double p_lpc = shfl_idx(lcur, t & 31);
+      const double target = val - p_lpc;
+      // ---- part A: needs only the tap warps' sums of the previous phase ----
+      double Bs = 0.0, As = 0.0, Ps = 0.0;
+      if (t) {
+        const double *sp = &S.sums[(t + 1) & 1][0][3 * li];
+        double b0 = sp[0], a0 = sp[1], q0 = sp[2];
+        double b1 = sp[12], a1 = sp[13], q1 = sp[14];
+#pragma unroll
+        for (int w = 2; w < CFG::tw; w += 2) {
+          b0 += sp[12 * w]; a0 += sp[12 * w + 1]; q0 += sp[12 * w + 2];
+          b1 += sp[12 * w + 12]; a1 += sp[12 * w + 13]; q1 += sp[12 * w + 14];
+        }
+        Bs = b0 + b1; As = a0 + a1; Ps = q0 + q1;
+      }
+      {                                                              // tap 0: mu_0 = pw_0 = 1 (ls.h:38-42)
+        double wn = fma(gprev, bp2, w0);
+        wn = fabs(wn) > 10.0 ? (wn > 0.0 ? 10.0 : -10.0) : wn;
+        w0 = wn;
+      }
+      const double p_mine = fma(bp1, w0, fma(gprev, As, Bs));
+      const double spow = fma(bp1, bp1, Ps);
+      const double rs = rcp_fast(spow + 1.0);
+      double p[kMixN];
+      p[0] = shfl_idx(p_mine, 0); p[1] = shfl_idx(p_mine, 1); p[2] = shfl_idx(p_mine, 2); p[3] = shfl_idx(p_mine, 3);
+      // ---- part B: needs the mix weights and the RLS prediction made after sample t-1 ----
+      if (t) bar_sync(kBarMR2S, 96);
+      p[4] = t ? ldd_vol(&S.p_rls) : 0.0;
+      const double sw0 = ldd_vol(&S.sw[0]), sw1 = ldd_vol(&S.sw[1]);
+      double ep0 = 0.0, ep1 = 0.0, wi[kMixN];
+#pragma unroll
+      for (int i = 0; i < kMixN; i++) {
+        const double v0 = ldd_vol(&S.v[0][i]), v1 = ldd_vol(&S.v[1][i]);
+        ep0 = fma(p[i], v0, ep0); ep1 = fma(p[i], v1, ep1);
+        wi[i] = fmax(fma(v1, sw1, v0 * sw0), 0.0);
+      }
+      if (!(fabs(ep0) <= 1.7976931348623157e308) || !(fabs(ep1) <= 1.7976931348623157e308)) bad = true;
+      const double p_lms = fma(ep1, sw1, ep0 * sw0);
+      const double px = p_lpc + p_lms;
+      double bp[kMixN];
+      {
+        double prefix = 0.0;
+#pragma unroll
+        for (int i = 0; i < kMixN; i++) {
+          const double pxi = fma(one_m_alpha, prefix, alpha * p_lms);
+          bp[i] = target - fmin(fmax(pxi, d.casc_lo), d.casc_hi);
+          prefix = fma(wi[i], p[i], prefix);
+        }
+      }
+      const double bpl = li == 0 ? bp[0] : (li == 1 ? bp[1] : (li == 2 ? bp[2] : bp[3]));
+      const double g = my_mu * (bpl - p_mine) * my_sp * rs;
+      if (own) {
+        S.g[t & 1][lane] = g;
+        const int np = pos == 0 ? myM - 1 : pos - 1;
+        myh[np] = bpl; myh[np + myM] = bpl;                          // mirrored ring: the window h + pos is always contiguous
+        pos = np;
+      }
+      bp2 = bp1; bp1 = bpl; gprev = g;
+      if (lane == 4) S.bp4 = bp[4];
+      if (lane >= 8 && lane < 8 + kMixN) { const int k = lane - 8; S.mx_p[k] = k == 0 ? p[0] : (k == 1 ? p[1] : (k == 2 ? p[2] : (k == 3 ? p[3] : p[4]))); }
+      if (lane == 16) { S.mx_ep[0] = ep0; S.mx_ep[1] = ep1; S.mx_target = target; S.pxq[t & 1] = px; }
+      __threadfence_block();
+      bar_arrive(kBarS2MR, 96);
+    }
+    bar_sync(kBarPhase, CFG::phase);
+  }
+  if (bad && lane == 0) atomicOr(&S.bad, 1);
+}
+
+// M: LS_ADA<L1>, LS_ADA<L2> (ls.h:223-237) on lanes 0..9, BlendExp (blend.h:50-90) on all lanes
+__device__ __forceinline__ void sg_mix_warp(SgShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n;
+  const int ex = lane < kMixN ? 0 : 1, i = min(lane - ex * kMixN, kMixN - 1);
+  const bool act = lane < 2 * kMixN;
+  double v = 1.0 / kMixN, eg = 0.0;                                  // own expert weight and AdaGrad state (LSInitType::Uniform)
+  double r0 = 0.0, r1 = 0.0;
+  const double beta = d.mix_beta, beta1 = 1.0 - d.mix_beta, mu = d.mu_mix;
+  for (int t = 0; t < n; t++) {
+    bar_sync(kBarS2MR, 96);
+    const double target = S.mx_target, ep0 = S.mx_ep[0], ep1 = S.mx_ep[1];
+    const double pi = S.mx_p[i];
+    {
+      const double er = target - (ex == 0 ? ep0 : ep1);
+      const double loss = ex == 0 ? sgn(er) : er;
+      const double grad = loss * pi;
+      eg = fma(beta, eg, beta1 * grad * grad);
+      v = fma(mu * rcp_fast(sqrt(eg) + 1e-5), grad, v);
+    }
+    r0 = fma(0.95, r0, (1.0 - 0.95) * (-fabs(target - ep0)));
+    r1 = fma(0.95, r1, (1.0 - 0.95) * (-fabs(target - ep1)));
+    const double mz = fmax(r0, r1);
+    const double e0 = c_exp(r0 - mz), e1 = c_exp(r1 - mz);
+    const double inv_total = rcp_fast(e0 + e1);
+    if (act) S.v[ex][i] = v;
+    if (lane == 16) { S.sw[0] = e0 * inv_total; S.sw[1] = e1 * inv_total; }
+    __threadfence_block();
+    if (t + 1 < n) bar_arrive(kBarMR2S, 96);
+  }
+}
+
+// R: RLS stage with adaptive forgetting (rls.cpp:17-65, rls.h:22-36). Lane j < m owns row j of P and w_j; x is replicated.
+// ph = P x and phi = x^T ph depend on state known before the sample's target bp4 arrives: they are computed ahead of it.
+__device__ __forceinline__ void sg_rls_warp(SgShared &S, const ChainDesc &d, int lane, double *xch)
+{
+  const int n = d.n, m = d.lm_n;
+  const int row = min(lane, m - 1);
+  double *rx = xch, *rph = xch + kMaxRls + 2;                        // x (history of the stage input), ph = P x: shared by the lanes
+  double P[kMaxRls];
+#pragma unroll
+  for (int k = 0; k < kMaxRls; k++) P[k] = (k == row) ? 1.0 : 0.0;
+  if (lane < kMaxRls + 2) { rx[lane] = 0.0; rph[lane] = 0.0; }
+  __syncwarp();
+  double w = 0.0, S0 = 0.0, S1 = 0.0, p_rls = 0.0;
+  const double gamma = d.lm_gamma;
+  for (int t = 0; t < n; t++) {
+    // ---- ahead of the sample: ph_row = P[row] . x, phi = x . ph ----
+    double phr = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxRls; k++) if (k < m) phr = fma(P[k], rx[k], phr);
+    if (lane < m) rph[lane] = phr;
+    __syncwarp();
+    double phi = 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxRls; k++) if (k < m) phi = fma(rx[k], rph[k], phi);
+    phi = fmax(phi, 1e-8);
+    const double Rr = fmax(S0 - S1, 1e-5);
+    const double rnis = rcp_fast(phi + Rr);
+    const double xprev = row > 0 ? rx[row - 1] : 0.0;                // x_new[row] for row > 0
+    bar_sync(kBarS2MR, 96);
+    const double bp4 = ldd_vol(&S.bp4);
+    const double err = bp4 - p_rls;
+    const double err2 = err * err;
+    const double mm = c_exp(-gamma * (err2 * rnis));
+    const double al = fma(0.999 - 0.99, mm, 0.99);
+    const double denom = rcp_fast(al + phi), inv_al = rcp_fast(al);
+    w = fma(err * denom, phr, w);                                    // w_row += err * denom * ph_row
+    // next prediction: sum_j x_new[j] w_new[j], x_new = [bp4, x_0 .. x_{m-2}]
+    const double xn = row > 0 ? xprev : bp4;
+    double term = lane < m ? xn * w : 0.0;
+    term += shfl_xor(term, 8); term += shfl_xor(term, 4); term += shfl_xor(term, 2); term += shfl_xor(term, 1);
+    p_rls = shfl_idx(term, 0);                                       // lanes 0..15 carry the sum over lanes 0..15 (m <= 10)
+    if (lane == 0) S.p_rls = p_rls;
+    __threadfence_block();
+    if (t + 1 < n) bar_arrive(kBarMR2S, 96);
+    // ---- off the critical path: P, x, S0, S1 ----
+    const double dp = denom * phr;
+#pragma unroll
+    for (int k = 0; k < kMaxRls; k++) if (k < m) P[k] = (P[k] - dp * rph[k]) * inv_al;
+    __syncwarp();                                                    // every lane has read rx / rph
+    if (lane < m) rx[lane] = xn;
+    __syncwarp();
+    S0 = fma(0.95, S0, (1.0 - 0.95) * err2);
+    S1 = fma(0.95, S1, (1.0 - 0.95) * phi);
+  }
+}
+
+// B: bias stage (bias.h:64-162), round / clamp / residual (libsac.cpp:105-108), cost sums; handles sample t-1 during phase t
+template <class CFG>
+__device__ __forceinline__ void sg_bias_warp(SgShared &S, const ChainDesc &d, int lane)
+{
+  const int n = d.n;
+  long long l1 = 0, sq = 0;
+  int32_t vcur = lane < n ? __ldg(d.own + lane) : 0;
+  int32_t vnext = 32 + lane < n ? __ldg(d.own + 32 + lane) : 0;
+  int32_t ebuf = 0;
+  const double nscale = (double)d.bias_nscale, bmu = d.bias_mu;
+  for (int ph = 0; ph <= n; ph++) {
+    if (ph > 0) {
+      const int t = ph - 1;
+      if ((t & 31) == 0 && t) { vcur = vnext; vnext = t + 32 + lane < n ? __ldg(d.own + t + 32 + lane) : 0; }
+      const int32_t vali = __shfl_sync(kFull, vcur, t & 31);
+      const double val = (double)vali;
+      const double px = S.pxq[t & 1];
+      int ctx0, ctx1, ctx2, mix_ctx;
+      {
+        const double h0 = S.hist_in[0], h1 = S.hist_in[1], h2 = S.hist_in[2];
+        const double d0 = S.hist_d[0], d1 = S.hist_d[1], d2 = S.hist_d[2], d3 = S.hist_d[3], d4 = S.hist_d[4];
+        const int b0 = h0 > px ? 0 : 1;
+        const int b2 = d0 < 0 ? 0 : 1, b3 = d1 < 0 ? 0 : 1, b4 = d2 < 0 ? 0 : 1;
+        const int b5 = d1 < d0 ? 0 : 1, b6 = d2 < d1 ? 0 : 1, b7 = d3 < d2 ? 0 : 1, b8 = d4 < d3 ? 0 : 1;
+        const int b9 = fabs(d0) > 32 ? 0 : 1;
+        const int b10 = 2 * h0 - h1 > px ? 0 : 1;
+        const int b11 = 3 * h0 - 3 * h1 + h2 > px ? 0 : 1;
+        const double sum = (fabs(d0) + fabs(d1) + fabs(d2) + fabs(d3) + fabs(d4)) * 0.2;
+        mix_ctx = sum > 512 ? 2 : (sum > 32 ? 1 : 0);
+        ctx0 = b0 + (b2 << 1) + (b9 << 2) + (b10 << 3) + (b11 << 4);
+        ctx1 = b2 + (b3 << 1) + (b4 << 2);
+        ctx2 = b5 + (b6 << 1) + (b7 << 2) + (b8 << 3);
+      }
+      const int tb = min(lane, 2);
+      const int myctx = tb == 0 ? ctx0 : (tb == 1 ? ctx1 : ctx2);
+      const double cv = S.cval[tb][myctx], cc = S.cnt[tb][myctx];
+      const double ptl = cv * rcp_fast(cc);
+      const double pt0 = shfl_idx(ptl, 0), pt1 = shfl_idx(ptl, 1), pt2 = shfl_idx(ptl, 2);
+      const double pbias = fma(pt2, S.mixw[mix_ctx][2], fma(pt1, S.mixw[mix_ctx][1], pt0 * S.mixw[mix_ctx][0]));
+      const double pd = px + pbias;
+      int32_t pi;
+      {
+        const double r = c_round(pd);
+        if (!(r >= (double)d.clamp_lo)) pi = d.clamp_lo;
+        else if (r > (double)d.clamp_hi) pi = d.clamp_hi;
+        else pi = (int32_t)r;
+      }
+      const int32_t e = vali - pi;
+      if ((t & 31) == lane) ebuf = e;
+      if ((t & 31) == 31 || t == n - 1) {
+        const int base = t & ~31;
+        if (base + lane <= t) d.resid[base + lane] = ebuf;
+      }
+      { const long long ae = e < 0 ? -(long long)e : (long long)e; l1 += ae; sq += (long long)e * (long long)e; }
+      {
+        const double delta = val - c_round(px);
+        const double bv = fmax(0.0, S.bvar), bm = S.bmean;
+        const double diff = delta - bm;
+        const double z = diff * diff * rcp_fast(bv + 1E-5);
+        const double wgt = c_exp(-0.5 * z);
+        double hin = 0.0, hdl = 0.0;
+        if (lane < 8) { hin = lane > 0 ? S.hist_in[lane - 1] : val; hdl = lane > 0 ? S.hist_d[lane - 1] : delta; }
+        __syncwarp();
+        if (lane < 8) { S.hist_in[lane] = hin; S.hist_d[lane] = hdl; }
+        if (lane < 3) {
+          double ncv = fma(wgt, delta, cv);
+          double ncc = cc + wgt;
+          if (ncc >= nscale) { ncv *= 0.5; ncc *= 0.5; }
+          S.cval[lane][myctx] = ncv; S.cnt[lane][myctx] = ncc;
+          const double ptv = lane == 0 ? pt0 : (lane == 1 ? pt1 : pt2);
+          S.mixw[mix_ctx][lane] += (bmu * sgn(delta - pbias)) * sgn(ptv);
+        }
+        if (lane == 0) {
+          const double nm = fma(0.998, bm, (1.0 - 0.998) * delta);
+          S.bvar = fma(0.998, S.bvar, (1.0 - 0.998) * ((delta - bm) * (delta - nm)));
+          S.bmean = nm;
+        }
+        __syncwarp();
+      }
+    }
+    bar_sync(kBarPhase, CFG::phase);
+  }
+  if (lane == 0) {
+    if (d.l1sum) *d.l1sum = l1;
+    if (d.sqsum) *d.sqsum = sq;
+  }
+}
+
+__host__ __device__ inline int sg_block_len(int N, int tap_threads)  // taps j = 1..N-1 in blocks of odd length over the tap threads
+{
+  const int taps = N - 1;
+  int L = (taps + tap_threads - 1) / tap_threads;
+  if (L < 1) L = 1;
+  return L | 1;
+}
+
+template <class CFG>
+__global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_sg_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
+  SgShared &S = *reinterpret_cast<SgShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double rls_xch[2 * kMaxRls + 4];                        // R: x (replicated history) and ph
+  if (tid == 0) {
+    const size_t head = (sizeof(SgShared) + 15) & ~size_t(15);
+    double *sp = reinterpret_cast<double *>(smem_raw + head);
+    const int regs[kStages] = {CFG::r0, CFG::r1, CFG::r2, CFG::r3};
+    for (int s = 0; s < kStages; s++) {
+      const int N = d.vn[s];
+      S.L[s] = sg_block_len(N, CFG::tap_threads);
+      S.h[s] = sp; sp += 2 * (N + 2);
+      S.mu[s] = sp; sp += N;
+      S.pw[s] = sp; sp += N;
+      if (S.L[s] > regs[s]) { S.wt[s] = sp; sp += N; } else S.wt[s] = nullptr;
+    }
+    S.clamped = 0; S.bad = 0;
+  }
+  {
+    double *z = reinterpret_cast<double *>(&S);
+    const int nz = (int)(offsetof(SgShared, h) / 8);
+    for (int i = tid; i < nz; i += CFG::threads) z[i] = 0.0;
+  }
+  __syncthreads();
+  for (int s = 0; s < kStages; s++) {
+    const int N = d.vn[s];
+    const double md = d.vmudecay[s], pd = d.vpowdecay[s];
+    double *h = S.h[s], *mu = S.mu[s], *pw = S.pw[s], *wt = S.wt[s];
+    for (int i = tid; i < N; i += CFG::threads) {
+      pw[i] = 1.0 / c_pow((double)(1 + i), pd);                      // ls.h:39 (the canonical table values)
+      mu[i] = c_pow(md, (double)i);                                  // ls.h:41
+      if (wt) wt[i] = 0.0;
+    }
+    for (int i = tid; i < 2 * (N + 2); i += CFG::threads) h[i] = 0.0;
+  }
+  __syncthreads();
+  if (tid < kStages) {                                               // sum_powtab accumulates sequentially (ls.h:40)
+    const double *pw = S.pw[tid];
+    const int N = d.vn[tid];
+    double sp = 0.0;
+    for (int i = 0; i < N; i++) sp += pw[i];
+    S.sum_pow[tid] = sp;
+  }
+  if (tid < 2 * kMixN) S.v[tid / kMixN][tid % kMixN] = 1.0 / kMixN;
+  if (tid < 2) S.sw[tid] = 0.5;
+  if (tid < 64) { S.cnt[0][tid] = 4.0; S.cnt[1][tid] = 4.0; S.cnt[2][tid] = 4.0; }
+  __syncthreads();
+  if (warp < CFG::tw) sg_tap_warps<CFG>(S, d, tid);
+  else if (warp == CFG::tw) sg_scalar_warp<CFG>(S, d, lane);
+  else if (warp == CFG::tw + 1) sg_mix_warp(S, d, lane);
+  else if (warp == CFG::tw + 2) sg_rls_warp(S, d, lane, rls_xch);
+  else sg_bias_warp<CFG>(S, d, lane);
+  __syncthreads();
+  if (tid == 0 && d.flags) *d.flags = (S.bad ? 1 : 0) | (S.clamped ? 2 : 0);
+}
+
+// =====================================================================================================================
+// OLS
+// =====================================================================================================================
+constexpr int kOT = 256;                                             // threads: 16 x 16 grid
+constexpr int kOXW = 256;                                            // input window (samples, power of two)
+constexpr int kOXS = 116;                                            // row stride of the regressor block (>= 16 * 7 + 1)
+constexpr int kOKB = 4;                                              // samples per block
+
+struct OlsSgShared {
+  double X[kOKB][kOXS];
+  double xo[kOXW], xq[kOXW];
+  double col[2][kOXS];
+  double pu[kOKB], ff[kOKB];
+  double wv[kMaxOls], z[kMaxOls];
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kOT, (NB <= 3 ? 3 : (NB <= 5 ? 2 : 1))) ols_sg_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
+  OlsSgShared &S = *reinterpret_cast<OlsSgShared *>(smem_raw);
+  double *Ls = reinterpret_cast<double *>(smem_raw + ((sizeof(OlsSgShared) + 15) & ~size_t(15)));   // L packed by rows: row k at k(k-1)/2
+  const int tid = threadIdx.x, lane = tid & 31, tw = tid >> 5;
+  const int r = tid >> 4, q = tid & 15;
+  const int N = d.n;
+  const int n = d.lenA + d.lenB, n1 = n + 1;
+  const double lambda = d.lambda, nu = d.nu, one_m_lambda = 1.0 - d.lambda;
+  constexpr int NP = NB * (NB + 1) / 2;
+  double cv[NP], wk[NP];
+  bool valid[NP];
+  {
+    int p = 0;
+#pragma unroll
+    for (int a = 0; a < NB; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++, p++) {
+        const int i = r + 16 * a, c = q + 16 * b;
+        valid[p] = i <= n && c <= i && c < n;
+        cv[p] = 0.0; wk[p] = 0.0;
+      }
+  }
+  for (int i = tid; i < kMaxOls; i += kOT) S.wv[i] = 0.0;
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;                               // w[lane], w[lane+32], w[lane+64] (every warp its copy)
+  double esum = 0.0;
+  int km = 0;
+  for (int qq = tid; qq < 192; qq += kOT) {
+    const int ix = qq - 64;
+    const bool in = ix >= 0 && ix < N;
+    S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+    S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+  }
+  int fill_end = 128;
+  int t = 0;
+  while (t < N) {
+    if (fill_end < t + 68) {
+      if (tid < 64) {
+        const int ix = fill_end + tid;
+        const bool in = ix < N;
+        S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+        S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+      }
+      fill_end += 64;
+    }
+    const int kb = min(min(kOKB, d.k - km), N - t);
+    __syncthreads();
+    // ---- regressors of the block: X[u][0..n), X[u][n] = sample (pred.cpp:17-31) ----
+    for (int e = tid; e < kb * n1; e += kOT) {
+      const int u = e / n1, j = e - u * n1;
+      const int tt = t + u;
+      const int sB = max(tt - d.lagB, d.minB) - d.backB;
+      double v;
+      if (j < d.lenA) v = S.xo[(tt - d.lenA + j) & (kOXW - 1)];
+      else if (j < n) v = S.xq[(sB + j - d.lenA) & (kOXW - 1)];
+      else v = S.xo[tt & (kOXW - 1)];
+      S.X[u][j] = v;
+    }
+    __syncthreads();
+    // ---- predictions: warp u takes sample u (ols.cpp:22-25) ----
+    if (tw < kb) {
+      double acc = 0.0;
+      if (lane < n) acc = fma(S.X[tw][lane], w0, acc);
+      if (lane + 32 < n) acc = fma(S.X[tw][lane + 32], w1, acc);
+      if (lane + 64 < n) acc = fma(S.X[tw][lane + 64], w2, acc);
+      acc = butterfly(acc);
+      if (lane == 0) { S.pu[tw] = acc; d.plpc[t + tw] = acc; }
+    }
+    __syncthreads();
+    // ---- IRLS weights (ols.cpp:29-36): serial running sum (every thread), one power per thread u < kb ----
+    {
+      double es_mine = 1.0;
+#pragma unroll
+      for (int u = 0; u < kOKB; u++)
+        if (u < kb) {
+          esum = fma(d.beta_sum, esum, fabs(S.X[u][n] - S.pu[u]));
+          if (tid == u) es_mine = esum;
+        }
+      if (tid < kb) S.ff[tid] = one_m_lambda * c_pow(es_mine + d.beta_add, -d.beta_pow);
+    }
+    __syncthreads();
+    // ---- covariance: the kb rank-1 updates of the block as one rank-kb update (ols.cpp:38-45) ----
+    km += kb;
+    const bool solve = km >= d.k;
+    {
+      double fu[kOKB], lamk = 1.0;
+#pragma unroll
+      for (int u = kOKB - 1; u >= 0; u--) { fu[u] = u < kb ? S.ff[u] * lamk : 0.0; if (u < kb) lamk *= lambda; }
+#pragma unroll
+      for (int p = 0; p < NP; p++) cv[p] *= lamk;
+#pragma unroll
+      for (int u = 0; u < kOKB; u++) {
+        if (u < kb) {                                                // uniform
+          double fx[NB], xc[NB];
+#pragma unroll
+          for (int a = 0; a < NB; a++) { fx[a] = fu[u] * S.X[u][min(r + 16 * a, n)]; xc[a] = S.X[u][min(q + 16 * a, n)]; }
+          int p = 0;
+#pragma unroll
+          for (int a = 0; a < NB; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++, p++) cv[p] = fma(fx[a], xc[b], cv[p]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NP; p++) cv[p] = valid[p] ? cv[p] : 0.0;
+    }
+    if (solve) {
+      km = 0;
+      {
+        int p = 0;
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+#pragma unroll
+          for (int b = 0; b <= a; b++, p++) wk[p] = cv[p] + ((a == b && r == q && r + 16 * a < n) ? nu : 0.0);
+      }
+      // ---- right-looking LDL^T of (C + nu I) augmented with b as row n; one column per step through S.col ----
+      if (q == 0) {                                                  // column 0 (b == 0 blocks are pairs (a,0))
+        int p = 0;
+#pragma unroll
+        for (int a = 0; a < NB; a++) { if (r + 16 * a <= n) S.col[0][r + 16 * a] = wk[p]; p += a + 1; }
+      }
+      __syncthreads();
+      bool ok = true;
+      for (int j = 0; j < n; j++) {
+        const double *cb = S.col[j & 1];
+        double *cn = S.col[(j + 1) & 1];
+        const double dj = cb[j];
+        if (dj < 1e-12) { ok = false; break; }
+        const double inv = rcp_fast(dj);
+        double li[NB], uc[NB];
+#pragma unroll
+        for (int a = 0; a < NB; a++) {
+          const int i = r + 16 * a, c = q + 16 * a;
+          li[a] = (i > j && i <= n) ? cb[i] * inv : 0.0;
+          uc[a] = (c > j && c < n) ? cb[c] : 0.0;
+        }
+        const int qn = (j + 1) & 15, bn = (j + 1) >> 4;
+        int p = 0;
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+#pragma unroll
+          for (int b = 0; b <= a; b++, p++) {
+            const int c = q + 16 * b;
+            if (valid[p] && c > j) {
+              const double v = fma(-li[a], uc[b], wk[p]);
+              wk[p] = v;
+              if (q == qn && b == bn) cn[r + 16 * a] = v;             // next column: rows >= j+1 (c = j+1)
+            }
+          }
+        if (q == 0) {                                                // L[i][j] = W[i][j] / d_j by rows; row n of L is z = D^-1 L^-1 b
+#pragma unroll
+          for (int a = 0; a < NB; a++) {
+            const int i = r + 16 * a;
+            if (i > j && i < n) Ls[(i * (i - 1)) / 2 + j] = li[a];
+            else if (i == n) S.z[j] = li[a];
+          }
+        }
+        __syncthreads();
+      }
+      if (ok && tw == 0) {
+        // back substitution L^T w = z, columns in descending order; row k of L is contiguous
+        double y0 = lane < n ? S.z[lane] : 0.0;
+        double y1 = lane + 32 < n ? S.z[lane + 32] : 0.0;
+        double y2 = lane + 64 < n ? S.z[lane + 64] : 0.0;
+        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
+        if (n >= 2) {
+          const double *row = Ls + ((n - 1) * (n - 2)) / 2;
+          l0 = lane < n - 1 ? row[lane] : 0.0; l1 = lane + 32 < n - 1 ? row[lane + 32] : 0.0; l2 = lane + 64 < n - 1 ? row[lane + 64] : 0.0;
+        }
+        for (int k = n - 1; k >= 1; k--) {
+          const double c0 = l0, c1 = l1, c2 = l2;
+          if (k >= 2) {                                              // next row, fetched one step ahead
+            const double *row = Ls + ((k - 1) * (k - 2)) / 2;
+            l0 = lane < k - 1 ? row[lane] : 0.0; l1 = lane + 32 < k - 1 ? row[lane + 32] : 0.0; l2 = lane + 64 < k - 1 ? row[lane + 64] : 0.0;
+          }
+          const int sl = k >> 5;
+          double yk = sl == 0 ? y0 : (sl == 1 ? y1 : y2);
+          yk = shfl_idx(yk, k & 31);
+          y0 = fma(-c0, yk, y0); y1 = fma(-c1, yk, y1); y2 = fma(-c2, yk, y2);   // rows beyond k-1 carry zeros
+        }
+        if (lane < n) S.wv[lane] = y0;
+        if (lane + 32 < n) S.wv[lane + 32] = y1;
+        if (lane + 64 < n) S.wv[lane + 64] = y2;
+      }
+      __syncthreads();
+      if (ok) {
+        w0 = lane < n ? S.wv[lane] : 0.0;
+        w1 = lane + 32 < n ? S.wv[lane + 32] : 0.0;
+        w2 = lane + 64 < n ? S.wv[lane + 64] : 0.0;
+      }
+    }
+    t += kb;
+  }
+}
+
+} // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+// shared memory a chain needs in cascade_sg_kernel<SMALL/LARGE>; 0 = not eligible for that variant
+size_t cascade_sg_smem_bytes(const int *vn, int large)
+{
+  const int regs_s[kStages] = {SgSmall::r0, SgSmall::r1, SgSmall::r2, SgSmall::r3};
+  const int regs_l[kStages] = {SgLarge::r0, SgLarge::r1, SgLarge::r2, SgLarge::r3};
+  size_t doubles = 0;
+  for (int s = 0; s < kStages; s++) {
+    const int N = vn[s], L = sg_block_len(N, large ? SgLarge::tap_threads : SgSmall::tap_threads);
+    doubles += 2 * (size_t)(N + 2) + 2 * (size_t)N;
+    if (!large && L > regs_s[s]) return 0;
+    if (large && L > regs_l[s]) doubles += (size_t)N;
+  }
+  return ((sizeof(SgShared) + 15) & ~size_t(15)) + doubles * 8 + 64;
+}
+int ols_sg_class(int n_ols) { const int nb = (n_ols + 1 + 15) / 16; return nb <= 3 ? 3 : (nb <= 5 ? 5 : 7); }
+size_t ols_sg_smem_bytes(int n_ols) { return ((sizeof(OlsSgShared) + 15) & ~size_t(15)) + (size_t)(n_ols * (n_ols - 1) / 2 + 8) * 8; }
+
+cudaError_t predictor_sg_init_attributes()
+{
+  const int big = 227 * 1024;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_sg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_sg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ols_sg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+}
+
+cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream)
+{
+  if (count <= 0) return cudaSuccess;
+  if (nb_class == 3) ols_sg_kernel<3><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
+  else if (nb_class == 5) ols_sg_kernel<5><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
+  else ols_sg_kernel<7><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
+  return cudaGetLastError();
+}
+cudaError_t launch_cascade_sg(const ChainDesc *d_descs, const int *d_idx, int count, int large, int smem_bytes, cudaStream_t stream)
+{
+  if (count <= 0) return cudaSuccess;
+  if (large) cascade_sg_kernel<SgLarge><<<count, SgLarge::threads, smem_bytes, stream>>>(d_descs, d_idx);
+  else cascade_sg_kernel<SgSmall><<<count, SgSmall::threads, smem_bytes, stream>>>(d_descs, d_idx);
+  return cudaGetLastError();
+}
+
+} // namespace sacb

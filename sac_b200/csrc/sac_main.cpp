@@ -80,7 +80,8 @@ static int list_file(const std::string &path, bool full, int mt_mode)
   std::printf("  WAVE  Codec: PCM (%d kbps)\n  %dHz %d Bit  %s\n  %u Samples [%s]\n", (int)std::round((sr * nch * bps) / 1000), sr, bits,
               nch == 1 ? "Mono" : "Stereo", ns, time_str(ns, sr).c_str());
   std::printf("  Profile: mt%d %ds\n  Ratio:   %.3f bps\n\n  Audio MD5: ", mt_mode, fl, bps);   // cmdline.cpp:307-311
-  size_t pos = 22 + md;
+  size_t pos = 22 + (size_t)md;
+  if (pos + 16 > b.size()) { std::printf("\nwarning: input is not a valid .sac file\n"); return 1; }   // metadata size beyond the file
   print_md5(&b[pos]);
   std::printf("\n");
   pos += 16;
@@ -251,6 +252,14 @@ int main(int argc, const char *argv[])
     if (!eng) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
     std::cout << "Create: '" << out << "': ";
     rc = sac_decode_file(eng, in.c_str(), out.c_str(), &st);
+    if (rc == SAC_E_MD5) {                                                                             // nothing was written: the audio is not the encoder's input
+      std::cout << "ok\n";
+      std::printf("\n  Audio MD5: Error ("); print_md5(st.md5); std::printf(")\n");
+      std::cerr << "error: " << sac_last_error() << "\n";
+      std::remove(out.c_str());
+      sac_engine_destroy(eng);
+      return 1;
+    }
     if (rc) { std::cout << "could not create\n"; std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
     std::cout << "ok\n";
     std::printf("  %d/%d: 100.0%%\n", st.numsamples, st.numsamples);

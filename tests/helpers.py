@@ -10,6 +10,15 @@ def sha(a):
     return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def reference_view(img):
+    """a .sac image (or its leading bytes) written by this library, as the reference would have written it: byte 17 of the
+    header names the arithmetic variant (1 = canonical, include/sac_b200.h); the reference writes 0 there"""
+    b = bytearray(img)
+    assert b[:4] == b"SAC2" and b[17] == 1, "files of this library carry arithmetic variant 1 in header byte 17"
+    b[17] = 0
+    return bytes(b)
+
+
 def case_profile(case, vmin, vmax, vdef):
     """same construction as tests/golden/make_golden.py"""
     if case["profile"] == "default":

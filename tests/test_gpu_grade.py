@@ -1,0 +1,145 @@
+"""-m gpu: the SEARCH-GRADE kernels (sac_b200/csrc/predictor_sg.cu) against the canonical kernels and the oracle.
+
+Search-grade evaluations only rank DDS candidates; they use the reference's formulas with free summation
+order, fused operations, reciprocals and a look-ahead schedule. Stated tolerance, checked here:
+  * residuals equal the canonical ones (= the oracle's, bit-exact) except in isolated samples where a prediction lies at a
+    rounding boundary: at most 1 sample in 10 000 may differ, each by one unit in either direction (+-1), plus whatever its echo
+    through the bias stage flips (same bound);
+  * objective values (bytes of the bitplane coder, entropy, L1) within 2e-4 relative of the canonical ones;
+  * the candidate ranking of recorded generations: same argmin, and any two candidates whose canonical costs differ by more
+    than 2e-4 relative keep their order;
+  * a frame encoded with a search-grade search is a canonical bitstream: it decodes bit-exact, and its record equals the
+    canonical-search record whenever both searches accept the same candidates.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import sac_b200 as sb
+from helpers import random_profile
+from synth_wav import synth_pcm
+
+pytestmark = pytest.mark.gpu
+FS = 20 * 44100
+IDX = np.array(sb.SEARCH_DIMS)
+
+
+def _dds_like_population(rng, vmin, vmax, vdef, P, pfrac=0.67, sigma=0.25):
+    lo, hi = vmin[IDX].astype(np.float64), vmax[IDX].astype(np.float64)
+    X = np.tile(vdef[IDX].astype(np.float64), (P, 1))
+    for p in range(1, P):
+        sel = rng.random(56) < pfrac
+        x = X[p] + sel * sigma * (hi - lo) * rng.standard_normal(56)
+        x = np.where(x < lo, np.minimum(lo + (lo - x), hi), x)
+        x = np.where(x > hi, np.maximum(hi - (x - hi), lo), x)
+        X[p] = x
+    return X
+
+
+def _profiles(X, vdef):
+    out = []
+    for x in X:
+        p = vdef.copy(); p[IDX] = x.astype(np.float32); out.append(p)
+    return out
+
+
+def _with_grade(engine, grade, fn):
+    prev = engine.set_grade(grade)
+    try:
+        return fn()
+    finally:
+        engine.set_grade(prev)
+
+
+def test_search_grade_residuals_equal_canonical_up_to_rounding_flips(engine):
+    vmin, vmax, vdef = sb.base_profile()
+    rng = np.random.default_rng(77)
+    pcm = synth_pcm(1, 2, 8).astype(np.int32)
+    planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])
+    win = engine.window(planes, mm)
+    big = vdef.copy(); big[28] = 6000; big[29] = 1500; big[31] = 3000; big[32] = 900; big[33] = 700; big[38] = 300; big[24] = 30; big[9] = 20; big[25] = 32; big[26] = 30; big[27] = 31
+    huge = vmax.copy()                                              # tables beyond shared memory: canonical cascade fallback
+    small = vmin.copy()
+    swapped = random_profile(rng, vmin, vmax); swapped[27] = -5.0
+    profs = [vdef, big, huge, small, swapped] + [random_profile(rng, vmin, vmax, cap0=None, cap1=None) for _ in range(6)]
+    n = 12000
+    s0 = engine.grade_stats()
+    canon, f0 = _with_grade(engine, 0, lambda: engine.predict(win, profs, 200, n, 4))
+    fast, f1 = _with_grade(engine, 1, lambda: engine.predict(win, profs, 200, n, 4))
+    s1 = engine.grade_stats()
+    e, rc = ol.oracle_predict(planes, mm, big, 4, 200, n)
+    assert np.array_equal(canon[1, 0], e[0]) and np.array_equal(canon[1, 1], e[1])     # the canonical side is the oracle's
+    assert s1[0] > s0[0] and s1[1] > s0[1] and s1[2] > s0[2], (s0, s1)                  # small, large and fallback all ran
+    for p in range(len(profs)):
+        assert (f1[p] & 1) == (f0[p] & 1), p
+        for ch in range(2):
+            d = fast[p, ch].astype(np.int64) - canon[p, ch].astype(np.int64)
+            nbad = int(np.count_nonzero(d))
+            assert nbad <= max(2, n // 10000 * 2) and (nbad == 0 or np.abs(d).max() <= 2), (p, ch, nbad, int(np.abs(d).max()))
+    win.close()
+
+
+def test_search_grade_edge_inputs(engine):
+    _, _, vdef = sb.base_profile()
+    sq = (np.where((np.arange(4000) // 50) % 2 == 0, 32767, -32768)).astype(np.int32)
+    for name, planes_raw in (("n1", [np.array([123], np.int32)]), ("n3", [np.array([5, -4, 9], np.int32)] * 2), ("silence", [np.zeros(3000, np.int32)] * 2),
+                             ("dc", [np.full(2000, -7, np.int32)]), ("fullscale", [sq, -sq]),
+                             ("ragged", [synth_pcm(1, 1, 3).astype(np.int32)[:2999, 0]])):
+        planes, means, mm = ol.analyse(planes_raw)
+        win = engine.window(planes, mm)
+        n = len(planes[0])
+        for k in (1, 3, 4):
+            fast, _ = _with_grade(engine, 1, lambda: engine.predict(win, [vdef], 0, n, k))
+            e, rc = ol.oracle_predict(planes, mm, vdef, k, 0, n)
+            for ch in range(len(planes)):
+                d = fast[0, ch].astype(np.int64) - e[ch].astype(np.int64)
+                assert np.count_nonzero(d) <= 2 and np.abs(d).max(initial=0) <= 2, (name, k, ch, int(np.count_nonzero(d)))
+        win.close()
+
+
+@pytest.mark.parametrize("cost_kind", [sb.COST_BITPLANE, sb.COST_ENTROPY, sb.COST_L1])
+def test_search_grade_costs_and_ranking_on_recorded_generations(engine, cost_kind):
+    vmin, vmax, vdef = sb.base_profile()
+    pcm = synth_pcm(2, 2, 5).astype(np.int32)
+    planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])
+    win = engine.window(planes, mm)
+    n, frm = 30000, 20000
+    for gen, (pfrac, sigma) in enumerate(((1.0, 0.25), (0.4, 0.2), (0.1, 0.1))):      # early, middle and late generations of a search
+        X = _dds_like_population(np.random.default_rng(100 + gen), vmin, vmax, vdef, 48, pfrac, sigma)
+        c0 = _with_grade(engine, 0, lambda: engine.eval_population(win, frm, n, vdef, X, cost_kind, 4))
+        c1 = _with_grade(engine, 1, lambda: engine.eval_population(win, frm, n, vdef, X, cost_kind, 4))
+        fin = np.isfinite(c0)
+        assert np.array_equal(fin, np.isfinite(c1))
+        rel = np.abs(c1[fin] - c0[fin]) / np.abs(c0[fin])
+        assert rel.max() <= 2e-4, (gen, float(rel.max()))
+        assert int(np.argmin(c1)) == int(np.argmin(c0)) or abs(c0[np.argmin(c1)] - c0.min()) <= 2e-4 * c0.min()
+        o = np.argsort(c0[fin]); a, b = c0[fin][o], c1[fin][o]
+        for i in range(len(a) - 1):                                  # order kept wherever the canonical gap exceeds the tolerance
+            later = b[i + 1:][a[i + 1:] - a[i] > 2e-4 * a[i]]
+            assert later.size == 0 or later.min() > b[i], (gen, i)
+        if cost_kind == sb.COST_BITPLANE:
+            assert np.mean(c1[fin] == c0[fin]) >= 0.5                # most candidates: not a single residual flips
+    # the oracle on one candidate of the last generation
+    prof = _profiles(X[3:4], vdef)[0]
+    e, _ = ol.oracle_predict(planes, mm, prof, 4, frm, n)
+    want = sum(ol.oracle_cost(cost_kind, e[ch]) for ch in range(2))
+    assert abs(c1[3] - want) <= 2e-4 * want
+    win.close()
+
+
+def test_frame_with_search_grade_search_is_a_canonical_bitstream(engine):
+    pcm = synth_pcm(0.5, 2, 5).astype(np.int32)
+    raw = [pcm[:, 0], pcm[:, 1]]
+    recs = []
+    for grade in (0, 1):
+        cfg = sb.make_cfg(None, optimize=1, fraction=0.004, maxnfunc=40, num_threads=0, spec=8, sigma=0.25, cost_kind=sb.COST_BITPLANE, grade=grade)
+        rec, prof = engine.frames_encode(cfg, [raw], FS)
+        dec, used = engine.frame_decode(2, rec, FS)
+        assert used == len(rec) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1]), grade
+        recs.append((rec, prof))
+    # same accepted sequence (costs agree except for isolated flips) -> the same profile and the same record; if a flip moved an
+    # acceptance the sizes still agree within the search tolerance
+    if np.array_equal(recs[0][1], recs[1][1]):
+        assert np.array_equal(recs[0][0], recs[1][0])
+    else:
+        assert abs(len(recs[0][0]) - len(recs[1][0])) <= 2e-3 * len(recs[0][0])

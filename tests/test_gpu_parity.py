@@ -291,3 +291,35 @@ def test_frame_encode_with_de_search_roundtrips(engine):
     assert used == len(rec2) and np.array_equal(dec[0], raw[0]) and np.array_equal(dec[1], raw[1])
     with pytest.raises(sb.SacError):
         engine.frames_encode(sb.make_cfg(None, optimize=1, fraction=0.25, maxnfunc=8, max_framelen=1, search=7), [raw], 44100)
+
+
+def test_decoder_refuses_corrupt_headers_and_never_delivers_unverified_audio(engine):
+    """untrusted input on the decode path: a bit plane count beyond the model's 32 planes, a frame capacity that overflows, an
+    unknown arithmetic variant, a damaged payload -- every one is an error (no output), never out-of-bounds work or silently
+    wrong audio (the audio MD5 decides, include/sac_b200.h)"""
+    pcm = synth_pcm(1, 2, 61).astype(np.int32)[:6000]
+    wav = _wav_bytes(pcm, sr=8000)
+    sac, st = engine.encode_memory(sb.make_cfg("normal", max_framelen=1), wav)
+    assert sac[17] == 1                                             # arithmetic variant: canonical
+    back, st2 = engine.decode_memory(sac, len(wav) + 64)
+    assert back == wav and st2.md5_ok == 1
+    mds = struct.unpack("<I", sac[18:22])[0]
+    first = 22 + mds + 16                                           # first frame record
+    blk = first + 4 + 58 * 4                                        # first block header: u32 size, 3 x i32, u16 flag
+    cases = {}
+    b = bytearray(sac); b[blk + 16] = 40; cases["bit plane count out of range"] = bytes(b)
+    b = bytearray(sac); b[blk + 16] = 31; cases["bit plane count out of range "] = bytes(b)
+    b = bytearray(sac); b[16] = 255; b[6:10] = struct.pack("<I", 0x7fffffff); cases["frame length out of range"] = bytes(b)
+    b = bytearray(sac); b[17] = 7; cases["unknown arithmetic variant"] = bytes(b)
+    b = bytearray(sac); b[blk + 18 + 40] ^= 0x55; cases["MD5 mismatch"] = bytes(b)
+    b = bytearray(sac); b[first:first + 4] = struct.pack("<I", 0x7fffffff); cases["bad sample count"] = bytes(b)
+    for what, img in cases.items():
+        with pytest.raises(sb.SacError, match=what.strip()):
+            engine.decode_memory(img, len(wav) + 64)
+    # a variant-0 file (what a reference build writes) is attempted: this short file decodes and verifies
+    b = bytearray(sac); b[17] = 0
+    back, st3 = engine.decode_memory(bytes(b), len(wav) + 64)
+    assert back == wav and st3.md5_ok == 1
+    # the engine is still usable after the refusals
+    back, _ = engine.decode_memory(sac, len(wav) + 64)
+    assert back == wav

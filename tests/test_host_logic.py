@@ -183,8 +183,16 @@ def test_container_prefix_and_frame_plan_match_the_reference_cli():
                 sb.container_plan(sb.make_cfg("normal"), wav)
             continue
         prefix, frames, st = sb.container_plan(sb.make_cfg("normal"), wav)
-        assert prefix.hex() == c["prefix_hex"], c["name"]
+        from helpers import reference_view
+        assert reference_view(prefix).hex() == c["prefix_hex"], c["name"]     # the reference's bytes but for the arithmetic-variant byte
         assert frames == c["frames"] and st.nframes == len(frames) and st.numsamples == sum(frames), c["name"]
+    # sample containers the codec cannot restore (24 valid bits in 32, a depth of 0 bits): refused, never coded as silence
+    assert len(g["refused_here"]) >= 2
+    for c in g["refused_here"]:
+        wav = wav_case(c["name"])
+        assert hashlib.sha1(wav).hexdigest() == c["wav_sha1"], c["name"]
+        with pytest.raises(sb.SacError, match="unsupported input format"):
+            sb.container_plan(sb.make_cfg("normal"), wav)
     # inputs the reference CLI refuses (cmdline.cpp:253-262, wav.cpp:196-203) are refused with an error, not coded
     bad = bytearray(wav_case("pcm16_stereo")); bad[20] = 3                       # WAVE_FORMAT_IEEE_FLOAT
     with pytest.raises(sb.SacError):
@@ -340,3 +348,52 @@ def test_frame_prologue_stats_equal_the_reference():
                 rf = ol.RefFrame(ref, 1, 1 << 24, zero_mean=zm)
                 rf.set_samples([s]); rf.analyse()
                 assert rf.stats(0)[:3] == got, (len(s), zm)
+
+
+def test_speculative_sequential_search_equals_run_single():
+    """sac_dds_run_spec: run_single in speculative batches -- accepted sequence, best cost and best vector equal the one-at-a-time
+    search for every batch width (the reference's sequential traces are pinned by the goldens above)"""
+    vmin, vmax, vdef = sb.base_profile()
+    idx = sb.SEARCH_DIMS
+    xmin, xmax, xs = vmin[idx].astype(float), vmax[idx].astype(float), vdef[idx].astype(float)
+    rng = np.random.default_rng(7)
+    tgt = xmin + (xmax - xmin) * rng.random(56)
+    wts = rng.random(56) + 0.1
+
+    def f(X):
+        Z = (X - tgt) / (xmax - xmin)
+        return (wts * Z * Z).sum(1) + 0.05 * np.abs(np.sin(37 * Z)).sum(1)
+
+    for nf, sigma in ((1, 0.2), (2, 0.2), (60, 0.25), (400, 0.2)):
+        seen = []
+
+        def g(X):
+            seen.append(X.copy()); return f(X)
+
+        b0, x0 = sb.dds_run(g, xmin, xmax, xs, nf, 0, sigma)
+        seq = np.concatenate(seen)
+        assert len(seq) == nf
+        for spec in (1, 2, 5, 16, 64):
+            batches = []
+
+            def h(X):
+                batches.append(X.copy()); return f(X)
+
+            b1, x1, ev = sb.dds_run_spec(h, xmin, xmax, xs, nf, sigma, spec)
+            assert b1 == b0 and np.array_equal(x1, x0), (nf, spec)
+            assert ev >= nf and ev == sum(len(b) for b in batches) and max(len(b) for b in batches) <= max(spec, 1) + 1
+            if spec == 1:
+                assert ev == nf and np.array_equal(np.concatenate(batches), seq)
+
+
+def test_speculative_search_with_ties_nan_and_constant_costs():
+    """costs that never improve, improve on every step, or are not finite: the walk over a batch stops at the FIRST success only"""
+    xmin, xmax, xs = np.zeros(5), np.ones(5), np.full(5, 0.5)
+    for fn in (lambda X: np.ones(len(X)), lambda X: X.sum(1), lambda X: np.where(X[:, 0] > 0.6, np.nan, X.sum(1)), lambda X: -np.arange(len(X), dtype=float) - X.sum(1)):
+        for nf in (7, 80):
+            b0, x0 = sb.dds_run(fn, xmin, xmax, xs, nf, 0, 0.2)
+            for spec in (3, 16):
+                if fn.__code__.co_consts and "arange" in fn.__code__.co_names:
+                    continue                                         # cost depends on the position in the batch: not a function of x
+                b1, x1, ev = sb.dds_run_spec(fn, xmin, xmax, xs, nf, 0.2, spec)
+                assert (b1 == b0 or (np.isnan(b1) and np.isnan(b0))) and np.array_equal(x1, x0), (nf, spec)
