@@ -1046,37 +1046,51 @@ double sparse_cost(const int32_t *buf, int n)
   return sum1 > 0 ? sum0 / sum1 : 0;
 }
 
-void push_state(std::vector<SubFrame> &sub, SubFrame &cur, int min_len, int block_state = -1, int samples_block = 0)
+// Adaptive split in three passes over plain data (the reference interleaves them in Codec::Analyse / PushState,
+// libsac.cpp:704-780; frame boundaries must come out identical, tests/golden/golden_split.json):
+//   1. class of every block of `blocksamples`: sparse (rank-mapped cost ratio above 1.35) or not;
+//   2. run-length encoding of the classes;
+//   3. runs -> sub-frames. A run becomes a sub-frame when the next run of the other class starts, unless it is shorter than
+//      min_len and a sub-frame already exists: then it is added to that sub-frame instead.
+// One behaviour of the reference is reproduced on purpose because it decides frame boundaries: when a short run is absorbed
+// like that, the reference keeps it as its open run and does not account the blocks of the run that follows -- each of them
+// adds the short run's length to the previous sub-frame once more -- and a later run of the short run's own class continues it.
+// With the codec's own parameters (blocks and minimum length both 3 s) only the ragged last block of a read can be short, and it
+// has no successor, so sub-frame lengths always add up to the samples read there.
+struct ClassRun { int state, length, nblocks; };
+
+std::vector<ClassRun> class_runs(const std::vector<std::vector<int32_t>> &samples, int blocksamples, int samples_read)
 {
-  if (block_state == cur.state) cur.length += samples_block;
-  else {
-    if (cur.length < min_len && sub.size()) sub.back().length += cur.length;      // extend the previous sub-frame
-    else {
-      sub.push_back(cur);
-      if (samples_block) { cur.state = block_state; cur.start += cur.length; cur.length = samples_block; }
-    }
+  std::vector<ClassRun> runs;
+  for (int done = 0; done < samples_read; done += blocksamples) {
+    const int len = std::min(blocksamples, samples_read - done);
+    double cost = 0;
+    for (const auto &plane : samples) cost += sparse_cost(plane.data() + done, len);
+    const int cls = (cost / (double)samples.size()) > 1.35;
+    if (!runs.empty() && runs.back().state == cls) { runs.back().length += len; runs.back().nblocks++; }
+    else runs.push_back({cls, len, 1});
   }
+  return runs;
 }
 
-// blocks of `blocksamples` are classed sparse (rank-mapped cost ratio above 1.35) or not; runs of equal class form the
-// sub-frames, a short tail joins its predecessor
 std::vector<SubFrame> analyse_subframes(const std::vector<std::vector<int32_t>> &samples, int blocksamples, int min_len, int samples_read)
 {
   std::vector<SubFrame> sub;
-  SubFrame cur;
-  int done = 0, nblock = 0;
-  while (done < samples_read) {
-    const int samples_block = std::min(blocksamples, samples_read - done);
-    double avg_cost = 0;
-    for (size_t ch = 0; ch < samples.size(); ch++) avg_cost += sparse_cost(samples[ch].data() + done, samples_block);
-    avg_cost /= (double)samples.size();
-    const int block_state = (avg_cost > 1.35);
-    if (nblock == 0) { cur.state = block_state; cur.length = samples_block; cur.start = 0; }
-    else push_state(sub, cur, min_len, block_state, samples_block);
-    done += samples_block;
-    nblock++;
+  const std::vector<ClassRun> runs = class_runs(samples, blocksamples, samples_read);
+  if (runs.empty()) return sub;
+  SubFrame open;
+  open.state = runs[0].state; open.start = 0; open.length = runs[0].length;
+  auto absorbed = [&](const SubFrame &r) { return r.length < min_len && !sub.empty(); };
+  for (size_t k = 1; k < runs.size(); k++) {
+    const ClassRun &r = runs[k];
+    if (r.state == open.state) open.length += r.length;                       // continues a short run that was absorbed before
+    else if (absorbed(open)) sub.back().length += open.length * r.nblocks;    // see above: once per block of the following run
+    else {
+      sub.push_back(open);
+      open.start += open.length; open.state = r.state; open.length = r.length;
+    }
   }
-  if (cur.length) push_state(sub, cur, min_len);
+  if (open.length) { if (absorbed(open)) sub.back().length += open.length; else sub.push_back(open); }
   return sub;
 }
 } // namespace

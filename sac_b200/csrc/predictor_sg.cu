@@ -83,6 +83,8 @@ struct SgShared {
   double p_rls;
   // B state (bias.h)
   double hist_in[8], hist_d[8], mixw[4][3], cnt[3][64], cval[3][64], bmean, bvar;
+  // R: x (history of the stage input) and ph = P x, shared by the lanes of the warp
+  double rls_xch[2 * kMaxRls + 4];
   // layout
   double *h[kStages], *mu[kStages], *pw[kStages], *wt[kStages];
   int L[kStages];
@@ -513,7 +515,6 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
   const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
   SgShared &S = *reinterpret_cast<SgShared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ double rls_xch[2 * kMaxRls + 4];                        // R: x (replicated history) and ph
   if (tid == 0) {
     const size_t head = (sizeof(SgShared) + 15) & ~size_t(15);
     double *sp = reinterpret_cast<double *>(smem_raw + head);
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
   if (warp < CFG::tw) sg_tap_warps<CFG>(S, d, tid);
   else if (warp == CFG::tw) sg_scalar_warp<CFG>(S, d, lane);
   else if (warp == CFG::tw + 1) sg_mix_warp(S, d, lane);
-  else if (warp == CFG::tw + 2) sg_rls_warp(S, d, lane, rls_xch);
+  else if (warp == CFG::tw + 2) sg_rls_warp(S, d, lane, S.rls_xch);
   else sg_bias_warp<CFG>(S, d, lane);
   __syncthreads();
   if (tid == 0 && d.flags) *d.flags = (S.bad ? 1 : 0) | (S.clamped ? 2 : 0);
