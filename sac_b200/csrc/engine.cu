@@ -326,13 +326,19 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     return SAC_OK;
   }
   // ---- search-grade kernels: OLS stages by matrix size class, cascades by what fits registers / shared memory ----
+  // (probe switch SACB_SG_PARTS: bit 0 = search-grade OLS, bit 1 = search-grade cascade; default both)
+  static const int sg_parts = [] { const char *v = std::getenv("SACB_SG_PARTS"); return v ? std::atoi(v) : 3; }();
   {
-    std::vector<int> ols_cls[3], casc[3];                           // OLS: 3 / 5 / 7 blocks; cascade: small, large, canonical fallback
-    size_t ols_sm[3] = {0, 0, 0}, casc_sm[3] = {0, 0, 0};
+    const int kOlsClasses = 6;
+    const int cls_id[kOlsClasses] = {16, 24, 32, 3, 5, 7};            // ols_sg_class values, cheapest first
+    std::vector<int> ols_cls[kOlsClasses], casc[3];                   // cascade: small, large, canonical fallback
+    size_t ols_sm[kOlsClasses] = {0, 0, 0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
     for (int v = 0; v < nv; v++) {
       const int u = ols_rep[v];
       const int n = ols_order(hps[slot_job[u]], slot_cc[u]);
-      const int c = ols_sg_class(n) == 3 ? 0 : (ols_sg_class(n) == 5 ? 1 : 2);
+      const int id = ols_sg_class(n);
+      int c = 0;
+      while (cls_id[c] != id) c++;
       ols_cls[c].push_back(nu + v);
       ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
     }
@@ -342,6 +348,7 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
       const size_t ss = cascade_sg_smem_bytes(vn, 0), sl = cascade_sg_smem_bytes(vn, 1);
       int c = 2;
       if (ss && ss <= kSmallCap) c = 0; else if (sl && sl <= kLargeCap) c = 1;
+      if (!(sg_parts & 2)) c = 2;
       casc[c].push_back(u);
       casc_sm[c] = std::max(casc_sm[c], c == 0 ? ss : (c == 1 ? sl : predictor_enc_shared_bytes() + (size_t)predictor_enc_smem_doubles(vn) * 8 + 64));
     }
@@ -349,14 +356,17 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     sg_stats[0] += (long long)casc[0].size(); sg_stats[1] += (long long)casc[1].size(); sg_stats[2] += (long long)casc[2].size();
     SACB_CUDA(h_idx.reserve((size_t)nu + nv));
     SACB_CUDA(d_idx.reserve((size_t)nu + nv));
-    size_t off = 0, ooff[3], coff[3];
-    for (int c = 0; c < 3; c++) { ooff[c] = off; for (int x : ols_cls[c]) h_idx.p[off++] = x; }
+    size_t off = 0, ooff[kOlsClasses], coff[3];
+    for (int c = 0; c < kOlsClasses; c++) { ooff[c] = off; for (int x : ols_cls[c]) h_idx.p[off++] = x; }
     for (int c = 0; c < 3; c++) { coff[c] = off; for (int x : casc[c]) h_idx.p[off++] = x; }
     SACB_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.p, sizeof(int) * off, cudaMemcpyHostToDevice, stream));
-    const int cls_nb[3] = {3, 5, 7};
-    for (int c = 2; c >= 0; c--)                                    // the longest-running class first
+    if (!(sg_parts & 1)) {                                          // canonical OLS kernel over all stages
+      SACB_CUDA(launch_predictor_enc(d_descs.p + nu, nv, d_descs.p, 0, casc_smem, ols_smem, stream, nullptr));
+      launches++; last_launches[0]++;
+    }
+    for (int c = kOlsClasses - 1; c >= 0 && (sg_parts & 1); c--)    // the longest-running class first
       if (!ols_cls[c].empty()) {
-        SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_nb[c], (int)ols_sm[c], stream));
+        SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_id[c], (int)ols_sm[c], stream));
         launches++; last_launches[0]++;
       }
     SACB_CUDA(cudaEventRecord(ev[4], stream));

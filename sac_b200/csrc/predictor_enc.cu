@@ -1024,6 +1024,7 @@ cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const C
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess) return e;
+  if (nchains <= 0) return cudaSuccess;                              // OLS stages alone
   cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs, nullptr);
   return cudaGetLastError();
 }

@@ -51,12 +51,15 @@ __device__ __forceinline__ double shfl_idx(double v, int l) { return __shfl_sync
 __device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
 __device__ __forceinline__ double ldd_vol(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
 
-// 1/x for normal x > 0: hardware seed (>= 20 bits) + two Newton steps
+// 1/x for normal x > 0: hardware seed (MUFU.RCP64H, about 8 good bits -- two Newton steps were measured to leave ~1e-9, which
+// compounds in the RLS matrix update) + three Newton steps, no special-case handling
 __device__ __forceinline__ double rcp_fast(double x)
 {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
@@ -77,8 +80,8 @@ struct SgShared {
   double pxq[2];                         // p_lpc + p_lms of sample t at [t&1] (for B)
   // S -> M, R (same sample)
   double mx_p[kMixN], mx_ep[2], mx_target, bp4;
-  // M -> S
-  double v[2][kMixN], eg[2][kMixN], sw[2], rsum[2];
+  // M -> S: expert weights, blend weights, and the combined stage weights max(sum_e s_e v_e[i], 0) (cascade.h:24-34)
+  double v[2][kMixN], sw[2], wi[kMixN];
   // R -> S
   double p_rls;
   // B state (bias.h)
@@ -87,7 +90,7 @@ struct SgShared {
   double rls_xch[2 * kMaxRls + 4];
   // layout
   double *h[kStages], *mu[kStages], *pw[kStages], *wt[kStages];
-  int L[kStages];
+  int L[kStages], M[kStages];            // taps per tap thread (odd), ring length
   double sum_pow[kStages];
   int clamped, bad;
 };
@@ -112,56 +115,129 @@ __device__ __forceinline__ double lds_a(uint32_t a) { double v; asm volatile("ld
 __device__ __forceinline__ void sts_a(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ double clamp10_flag(double wn, bool &clamped)
+// e^x for x <= 0 (all uses: softmax of losses, forgetting factor, bias gate): k = rint(x log2 e), degree-13 Taylor polynomial in
+// Estrin form (dependent depth 5 instead of Horner's 13), 2^k by exponent arithmetic; below 2^-1000 the result is 0
+__device__ __forceinline__ double exp_neg(double x)
 {
-  const bool c = fabs(wn) > 10.0;
-  clamped |= c;
-  return c ? (wn > 0.0 ? 10.0 : -10.0) : wn;
+  const double kd = rint(x * 0x1.71547652b82fep+0);
+  double r = fma(-kd, 0x1.62e42fee00000p-1, x);
+  r = fma(-kd, 0x1.a39ef35793c76p-33, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p01 = fma(r, 1.0, 1.0), p23 = fma(r, 0x1.5555555555555p-3, 0.5), p45 = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);
+  const double p67 = fma(r, 0x1.a01a01a01a01ap-13, 0x1.6c16c16c16c17p-10), p89 = fma(r, 0x1.71de3a556c734p-19, 0x1.a01a01a01a01ap-16);
+  const double pab = fma(r, 0x1.ae64567f544e4p-26, 0x1.27e4fb7789f5cp-22), pcd = fma(r, 0x1.6124613a86d09p-33, 0x1.1eed8eff8d898p-29);
+  const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
+  const double o0 = fma(r4, q1, q0), o1 = fma(r4, pcd, q2);
+  const double p = fma(r8, o1, o0);
+  const int k = (int)kd;
+  if (k < -1000) return 0.0;
+  return __longlong_as_double(__double_as_longlong(p) + ((long long)k << 52));
 }
 
-// one register slot of a tap thread: weight update of the previous sample, then the three look-ahead sums.
-// ah -> h_{j0}(t), amu -> mu[j0], apw -> pw[j0]; slot Q is tap j0 + Q: h_{j+1}(t) = h_j(t-1) feeds the update.
-template <int R, int Q> struct TapSlots {
-  static __device__ __forceinline__ void run(double (&w)[R], uint32_t ah, uint32_t amu, uint32_t apw, int cnt, double gprev, double &hm, double &hc,
-                                             double &aB, double &aA, double &aP, bool &clamped)
+// one tap: weight update of the previous sample (the clamp is only DETECTED: a chain that meets it is re-evaluated by the
+// canonical kernel), then the three look-ahead sums. hp = h_{j+1}(t) = h_j(t-1), hc = h_j(t), hm = h_{j-1}(t).
+__device__ __forceinline__ void tap_one(double &w, double hp, double hc, double hm, double m, double pwj, double gprev, double &aB, double &aA,
+                                        double &aP, bool &clamped)
+{
+  const double wn = fma(m * gprev, hp, w);
+  clamped |= fabs(wn) > 10.0;
+  w = wn;
+  aB = fma(hm, wn, aB);
+  aA = fma(m * hc, hm, aA);
+  aP = fma(pwj, hm * hm, aP);
+}
+
+// L taps of one thread, exact length (tables and ring are padded with zeros up to a whole block: no predicates)
+template <int R, int L, int Q> struct TapBlock {
+  static __device__ __forceinline__ void run(double (&w)[R], uint32_t ah, uint32_t amu, uint32_t apw, double gprev, double hm, double hc, double &aB,
+                                             double &aA, double &aP, bool &clamped)
   {
-    if constexpr (Q < R) {
-      if (Q < cnt) {
-        const double hp = lds_o<8 * (Q + 1)>(ah);
-        const double m = lds_o<8 * Q>(amu);
-        const double wn = clamp10_flag(fma(m * gprev, hp, w[Q]), clamped);
-        w[Q] = wn;
-        aB = fma(hm, wn, aB);
-        aA = fma(m * hc, hm, aA);
-        aP = fma(lds_o<8 * Q>(apw), hm * hm, aP);
-        hm = hc; hc = hp;
-      }
-      TapSlots<R, Q + 1>::run(w, ah, amu, apw, cnt, gprev, hm, hc, aB, aA, aP, clamped);
+    if constexpr (Q < L && Q < R) {
+      const double hp = lds_o<8 * (Q + 1)>(ah);
+      tap_one(w[Q], hp, hc, hm, lds_o<8 * Q>(amu), lds_o<8 * Q>(apw), gprev, aB, aA, aP, clamped);
+      TapBlock<R, L, Q + 1>::run(w, ah, amu, apw, gprev, hc, hp, aB, aA, aP, clamped);
     }
   }
 };
+template <int R, int L>
+__device__ __forceinline__ void tap_block(double (&w)[R], uint32_t ah, uint32_t amu, uint32_t apw, double gprev, double &aB, double &aA, double &aP,
+                                          bool &clamped)
+{
+  TapBlock<R, L, 0>::run(w, ah, amu, apw, gprev, lds_o<-8>(ah), lds_o<0>(ah), aB, aA, aP, clamped);
+}
 
-// one stage of one tap thread for one sample. hw = shared address of h_0(t) (window start), tables at amu0 / apw0 / awt0
-// (index 0); taps j0 .. jn-1 of this thread, the first R of them with register-resident weights.
+// one stage of one tap thread for one sample. hw = shared address of h_0(t); tables at amu0 / apw0 / awt0 (index 0); this
+// thread's block starts at tap j0 and has L taps (odd, uniform over the CTA), the first R of them in registers.
 template <int R>
-__device__ __forceinline__ void tap_stage(double (&w)[R], uint32_t hw, uint32_t amu0, uint32_t apw0, uint32_t awt0, int j0, int cnt, double gprev,
+__device__ __forceinline__ void tap_stage(double (&w)[R], uint32_t hw, uint32_t amu0, uint32_t apw0, uint32_t awt0, int j0, int L, double gprev,
                                           double &aB, double &aA, double &aP, bool &clamped)
 {
-  if (cnt <= 0) return;
-  const uint32_t ah = hw + 8u * (uint32_t)j0, amu = amu0 + 8u * (uint32_t)j0, apw = apw0 + 8u * (uint32_t)j0;
-  double hm = lds_o<-8>(ah), hc = lds_o<0>(ah);
-  TapSlots<R, 0>::run(w, ah, amu, apw, cnt, gprev, hm, hc, aB, aA, aP, clamped);
-  for (int q = R; q < cnt; q++) {                                   // block longer than the register slots: weights in shared memory
-    const uint32_t o = 8u * (uint32_t)q;
-    const double hp = lds_a(ah + o + 8u);
-    const double m = lds_a(amu + o);
-    const uint32_t aw = awt0 + 8u * (uint32_t)j0 + o;
-    const double wn = clamp10_flag(fma(m * gprev, hp, lds_a(aw)), clamped);
-    sts_a(aw, wn);
-    aB = fma(hm, wn, aB);
-    aA = fma(m * hc, hm, aA);
-    aP = fma(lds_a(apw + o), hm * hm, aP);
-    hm = hc; hc = hp;
+  const uint32_t o0 = 8u * (uint32_t)j0;
+  const uint32_t ah = hw + o0, amu = amu0 + o0, apw = apw0 + o0;
+  switch (L < R ? L : R) {                                           // uniform branch; odd lengths only (sg_block_len)
+    case 1: tap_block<R, 1>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 3: if constexpr (R >= 3) tap_block<R, 3>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 5: if constexpr (R >= 5) tap_block<R, 5>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 7: if constexpr (R >= 7) tap_block<R, 7>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 9: if constexpr (R >= 9) tap_block<R, 9>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 11: if constexpr (R >= 11) tap_block<R, 11>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 13: if constexpr (R >= 13) tap_block<R, 13>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 15: if constexpr (R >= 15) tap_block<R, 15>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 17: if constexpr (R >= 17) tap_block<R, 17>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 19: if constexpr (R >= 19) tap_block<R, 19>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    case 21: if constexpr (R >= 21) tap_block<R, 21>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
+    default: break;
+  }
+  if (L > R) {                                                       // block longer than the register slots: weights in shared memory
+    double hm = lds_a(ah + 8u * (uint32_t)(R - 1)), hc = lds_a(ah + 8u * (uint32_t)R);
+    for (int q = R; q < L; q++) {
+      const uint32_t o = 8u * (uint32_t)q;
+      const double hp = lds_a(ah + o + 8u);
+      const uint32_t aw = awt0 + o0 + o;
+      double wv = lds_a(aw);
+      tap_one(wv, hp, hc, hm, lds_a(amu + o), lds_a(apw + o), gprev, aB, aA, aP, clamped);
+      sts_a(aw, wv);
+      hm = hc; hc = hp;
+    }
+  }
+}
+
+// NV values per lane summed over the warp: at each of the first levels a lane keeps half of its values and trades the other
+// half with its partner; value q ends up in the lanes whose upper bits spell q. Writes sums[base + q].
+template <int NV>
+__device__ __forceinline__ void warp_sums(const double (&acc)[12], int first, int lane, double *out)
+{
+  static_assert(NV == 8 || NV == 16, "padded value count");
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  if constexpr (NV == 16) {
+    double a8[8], a4[4], a2[2], a1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double lo = acc[k], hi = k + 8 < 12 ? acc[k + 8] : 0.0;
+      a8[k] = (b4 ? hi : lo) + shfl_xor(b4 ? lo : hi, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) a4[k] = (b3 ? a8[4 + k] : a8[k]) + shfl_xor(b3 ? a8[k] : a8[4 + k], 8);
+#pragma unroll
+    for (int k = 0; k < 2; k++) a2[k] = (b2 ? a4[2 + k] : a4[k]) + shfl_xor(b2 ? a4[k] : a4[2 + k], 4);
+    a1 = (b1 ? a2[1] : a2[0]) + shfl_xor(b1 ? a2[0] : a2[1], 2);
+    a1 = a1 + shfl_xor(a1, 1);
+    const int slot = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+    if ((lane & 1) == 0 && slot < 12) out[slot] = a1;
+  } else {                                                           // the first six values only (stages 0 and 1)
+    double a4[4], a2[2], a1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double lo = acc[first + k], hi = k + 4 < 6 ? acc[first + k + 4] : 0.0;
+      a4[k] = (b4 ? hi : lo) + shfl_xor(b4 ? lo : hi, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) a2[k] = (b3 ? a4[2 + k] : a4[k]) + shfl_xor(b3 ? a4[k] : a4[2 + k], 8);
+    a1 = (b2 ? a2[1] : a2[0]) + shfl_xor(b2 ? a2[0] : a2[1], 4);
+    a1 = a1 + shfl_xor(a1, 2);
+    a1 = a1 + shfl_xor(a1, 1);
+    const int slot = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    if ((lane & 3) == 0 && slot < 6) out[first + slot] = a1;
   }
 }
 
@@ -170,17 +246,19 @@ __device__ __forceinline__ void sg_tap_warps(SgShared &S, const ChainDesc &d, in
 {
   const int lane = tid & 31, tw = tid >> 5;
   const int n = d.n;
-  int M[kStages], j0[kStages], cnt[kStages], pos[kStages];
+  int M[kStages], j0[kStages], L[kStages], pos[kStages];
+  bool mine[kStages];                                                // this thread has a block of the stage
   uint32_t ah[kStages], amu[kStages], apw[kStages], awt[kStages];
 #pragma unroll
   for (int s = 0; s < kStages; s++) {
-    const int N = d.vn[s], L = S.L[s];
-    M[s] = N + 2;
-    j0[s] = 1 + tid * L;
-    cnt[s] = min(j0[s] + L, N) - j0[s];                             // <= 0: no taps of this stage on this thread
+    L[s] = S.L[s]; M[s] = S.M[s];
+    j0[s] = 1 + tid * L[s];
+    mine[s] = j0[s] < d.vn[s];
     pos[s] = 0;                                                      // ring position of h_0(t)
     ah[s] = smem_u32(S.h[s]); amu[s] = smem_u32(S.mu[s]); apw[s] = smem_u32(S.pw[s]); awt[s] = S.wt[s] ? smem_u32(S.wt[s]) : 0u;
   }
+  // stages 2 and 3 are short (default 32 and 4 taps): most warps hold none of their taps and sum six values instead of twelve
+  const bool wide = (1 + (tw * 32) * L[2] < d.vn[2]) || (1 + (tw * 32) * L[3] < d.vn[3]);
   double w0[CFG::r0], w1[CFG::r1], w2[CFG::r2], w3[CFG::r3];
 #pragma unroll
   for (int q = 0; q < CFG::r0; q++) w0[q] = 0.0;
@@ -194,32 +272,17 @@ __device__ __forceinline__ void sg_tap_warps(SgShared &S, const ChainDesc &d, in
   for (int t = 0; t <= n; t++) {
     if (t < n) {
       const double *gp = S.g[(t + 1) & 1];                           // g(t-1)
-      const double g0 = ldd_vol(gp), g1 = ldd_vol(gp + 1), g2 = ldd_vol(gp + 2), g3 = ldd_vol(gp + 3);
       double acc[12];
 #pragma unroll
       for (int q = 0; q < 12; q++) acc[q] = 0.0;
-      tap_stage<CFG::r0>(w0, ah[0] + 8u * (uint32_t)pos[0], amu[0], apw[0], awt[0], j0[0], cnt[0], g0, acc[0], acc[1], acc[2], clamped);
-      tap_stage<CFG::r1>(w1, ah[1] + 8u * (uint32_t)pos[1], amu[1], apw[1], awt[1], j0[1], cnt[1], g1, acc[3], acc[4], acc[5], clamped);
-      tap_stage<CFG::r2>(w2, ah[2] + 8u * (uint32_t)pos[2], amu[2], apw[2], awt[2], j0[2], cnt[2], g2, acc[6], acc[7], acc[8], clamped);
-      tap_stage<CFG::r3>(w3, ah[3] + 8u * (uint32_t)pos[3], amu[3], apw[3], awt[3], j0[3], cnt[3], g3, acc[9], acc[10], acc[11], clamped);
-      // twelve butterflies in one: at each of the first four levels a lane keeps half of its (padded to 16) values and
-      // trades the other half with its partner; value q ends up in the lane pair whose bits 4..1 spell q
-      {
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-        double a8[8], a4[4], a2[2], a1;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const double lo = acc[k], hi = k + 8 < 12 ? acc[k + 8] : 0.0;
-          a8[k] = (b4 ? hi : lo) + shfl_xor(b4 ? lo : hi, 16);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) a4[k] = (b3 ? a8[4 + k] : a8[k]) + shfl_xor(b3 ? a8[k] : a8[4 + k], 8);
-#pragma unroll
-        for (int k = 0; k < 2; k++) a2[k] = (b2 ? a4[2 + k] : a4[k]) + shfl_xor(b2 ? a4[k] : a4[2 + k], 4);
-        a1 = (b1 ? a2[1] : a2[0]) + shfl_xor(b1 ? a2[0] : a2[1], 2);
-        a1 = a1 + shfl_xor(a1, 1);
-        const int slot = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-        if ((lane & 1) == 0 && slot < 12) S.sums[t & 1][tw][slot] = a1;
+      if (mine[0]) tap_stage<CFG::r0>(w0, ah[0] + 8u * (uint32_t)pos[0], amu[0], apw[0], awt[0], j0[0], L[0], ldd_vol(gp), acc[0], acc[1], acc[2], clamped);
+      if (mine[1]) tap_stage<CFG::r1>(w1, ah[1] + 8u * (uint32_t)pos[1], amu[1], apw[1], awt[1], j0[1], L[1], ldd_vol(gp + 1), acc[3], acc[4], acc[5], clamped);
+      if (wide) {
+        if (mine[2]) tap_stage<CFG::r2>(w2, ah[2] + 8u * (uint32_t)pos[2], amu[2], apw[2], awt[2], j0[2], L[2], ldd_vol(gp + 2), acc[6], acc[7], acc[8], clamped);
+        if (mine[3]) tap_stage<CFG::r3>(w3, ah[3] + 8u * (uint32_t)pos[3], amu[3], apw[3], awt[3], j0[3], L[3], ldd_vol(gp + 3), acc[9], acc[10], acc[11], clamped);
+        warp_sums<16>(acc, 0, lane, &S.sums[t & 1][tw][0]);
+      } else {
+        warp_sums<8>(acc, 0, lane, &S.sums[t & 1][tw][0]);             // slots 6..11 of this warp stay zero
       }
 #pragma unroll
       for (int s = 0; s < kStages; s++) pos[s] = pos[s] == 0 ? M[s] - 1 : pos[s] - 1;   // S pushes bp(t) at this slot during the same phase
@@ -237,9 +300,10 @@ __device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, 
   const double alpha = d.proj_alpha, one_m_alpha = 1.0 - d.proj_alpha;
   const int li = lane & 3;                                           // lanes >= 4 shadow lanes 0..3 (results unused)
   const bool own = lane < kStages;
-  const int myM = d.vn[li] + 2;
+  const int myM = S.M[li];
   double *myh = S.h[li];
   const double my_mu = d.vmu[li], my_sp = S.sum_pow[li];
+  const double clo = d.casc_lo, chi = d.casc_hi;
   int pos = 0;
   double w0 = 0.0, bp1 = 0.0, bp2 = 0.0, gprev = 0.0;                // tap 0 of stage li, bp(t-1), bp(t-2), g(t-1)
   bool bad = false;
@@ -276,34 +340,40 @@ __device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, 
         w0 = wn;
       }
       const double p_mine = fma(bp1, w0, fma(gprev, As, Bs));
-      const double spow = fma(bp1, bp1, Ps);
-      const double rs = rcp_fast(spow + 1.0);
+      const double rs = rcp_fast(fma(bp1, bp1, Ps) + 1.0);           // 1 / (spow + 1)
       double p[kMixN];
       p[0] = shfl_idx(p_mine, 0); p[1] = shfl_idx(p_mine, 1); p[2] = shfl_idx(p_mine, 2); p[3] = shfl_idx(p_mine, 3);
       // ---- part B: needs the mix weights and the RLS prediction made after sample t-1 ----
       if (t) bar_sync(kBarMR2S, 96);
       p[4] = t ? ldd_vol(&S.p_rls) : 0.0;
       const double sw0 = ldd_vol(&S.sw[0]), sw1 = ldd_vol(&S.sw[1]);
-      double ep0 = 0.0, ep1 = 0.0, wi[kMixN];
+      double e0a = 0.0, e0b = 0.0, e1a = 0.0, e1b = 0.0, wi[kMixN];
 #pragma unroll
       for (int i = 0; i < kMixN; i++) {
         const double v0 = ldd_vol(&S.v[0][i]), v1 = ldd_vol(&S.v[1][i]);
-        ep0 = fma(p[i], v0, ep0); ep1 = fma(p[i], v1, ep1);
-        wi[i] = fmax(fma(v1, sw1, v0 * sw0), 0.0);
+        if (i & 1) { e0b = fma(p[i], v0, e0b); e1b = fma(p[i], v1, e1b); } else { e0a = fma(p[i], v0, e0a); e1a = fma(p[i], v1, e1a); }
+        wi[i] = ldd_vol(&S.wi[i]);
       }
+      const double ep0 = e0a + e0b, ep1 = e1a + e1b;
       if (!(fabs(ep0) <= 1.7976931348623157e308) || !(fabs(ep1) <= 1.7976931348623157e308)) bad = true;
       const double p_lms = fma(ep1, sw1, ep0 * sw0);
-      const double px = p_lpc + p_lms;
       double bp[kMixN];
       {
+        const double apl = alpha * p_lms;
         double prefix = 0.0;
 #pragma unroll
         for (int i = 0; i < kMixN; i++) {
-          const double pxi = fma(one_m_alpha, prefix, alpha * p_lms);
-          bp[i] = target - fmin(fmax(pxi, d.casc_lo), d.casc_hi);
+          bp[i] = target - fmin(fmax(fma(one_m_alpha, prefix, apl), clo), chi);
           prefix = fma(wi[i], p[i], prefix);
         }
       }
+      // what M and R wait for goes out first
+      if (lane == 4) S.bp4 = bp[4];
+      if (lane >= 8 && lane < 8 + kMixN) { const int k = lane - 8; S.mx_p[k] = k == 0 ? p[0] : (k == 1 ? p[1] : (k == 2 ? p[2] : (k == 3 ? p[3] : p[4]))); }
+      if (lane == 16) { S.mx_ep[0] = ep0; S.mx_ep[1] = ep1; S.mx_target = target; }
+      __threadfence_block();
+      bar_arrive(kBarS2MR, 96);
+      // ... then what the tap warps and B need at the next phase
       const double bpl = li == 0 ? bp[0] : (li == 1 ? bp[1] : (li == 2 ? bp[2] : bp[3]));
       const double g = my_mu * (bpl - p_mine) * my_sp * rs;
       if (own) {
@@ -312,12 +382,8 @@ __device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, 
         myh[np] = bpl; myh[np + myM] = bpl;                          // mirrored ring: the window h + pos is always contiguous
         pos = np;
       }
+      if (lane == 16) S.pxq[t & 1] = p_lpc + p_lms;
       bp2 = bp1; bp1 = bpl; gprev = g;
-      if (lane == 4) S.bp4 = bp[4];
-      if (lane >= 8 && lane < 8 + kMixN) { const int k = lane - 8; S.mx_p[k] = k == 0 ? p[0] : (k == 1 ? p[1] : (k == 2 ? p[2] : (k == 3 ? p[3] : p[4]))); }
-      if (lane == 16) { S.mx_ep[0] = ep0; S.mx_ep[1] = ep1; S.mx_target = target; S.pxq[t & 1] = px; }
-      __threadfence_block();
-      bar_arrive(kBarS2MR, 96);
     }
     bar_sync(kBarPhase, CFG::phase);
   }
@@ -347,17 +413,22 @@ __device__ __forceinline__ void sg_mix_warp(SgShared &S, const ChainDesc &d, int
     r0 = fma(0.95, r0, (1.0 - 0.95) * (-fabs(target - ep0)));
     r1 = fma(0.95, r1, (1.0 - 0.95) * (-fabs(target - ep1)));
     const double mz = fmax(r0, r1);
-    const double e0 = c_exp(r0 - mz), e1 = c_exp(r1 - mz);
+    const double e0 = exp_neg(r0 - mz), e1 = exp_neg(r1 - mz);
     const double inv_total = rcp_fast(e0 + e1);
+    const double s0 = e0 * inv_total, s1 = e1 * inv_total;
+    // combined stage weight of input i: both experts' new weights meet in lane i
+    const double vo = __shfl_sync(kFull, v, (lane + kMixN) & 31);    // lane i < 5 receives expert 1's weight of input i
     if (act) S.v[ex][i] = v;
-    if (lane == 16) { S.sw[0] = e0 * inv_total; S.sw[1] = e1 * inv_total; }
+    if (lane < kMixN) S.wi[lane] = fmax(fma(vo, s1, v * s0), 0.0);
+    if (lane == 16) { S.sw[0] = s0; S.sw[1] = s1; }
     __threadfence_block();
     if (t + 1 < n) bar_arrive(kBarMR2S, 96);
   }
 }
 
-// R: RLS stage with adaptive forgetting (rls.cpp:17-65, rls.h:22-36). Lane j < m owns row j of P and w_j; x is replicated.
-// ph = P x and phi = x^T ph depend on state known before the sample's target bp4 arrives: they are computed ahead of it.
+// R: RLS stage with adaptive forgetting (rls.cpp:17-65, rls.h:22-36). Lane j < m owns row j of P and w_j. Everything that
+// does not depend on the sample's stage input bp4 is computed ahead of it: ph = P x, phi = x^T ph, and the two dot products
+// of the NEXT prediction  p(t+1) = x_new . (w + c ph) = bp4 (w_0 + c ph_0) + Q1 + c Q2,  x_new = [bp4, x_0 .. x_{m-2}].
 __device__ __forceinline__ void sg_rls_warp(SgShared &S, const ChainDesc &d, int lane, double *xch)
 {
   const int n = d.n, m = d.lm_n;
@@ -371,7 +442,6 @@ __device__ __forceinline__ void sg_rls_warp(SgShared &S, const ChainDesc &d, int
   double w = 0.0, S0 = 0.0, S1 = 0.0, p_rls = 0.0;
   const double gamma = d.lm_gamma;
   for (int t = 0; t < n; t++) {
-    // ---- ahead of the sample: ph_row = P[row] . x, phi = x . ph ----
     double phr = 0.0;
 #pragma unroll
     for (int k = 0; k < kMaxRls; k++) if (k < m) phr = fma(P[k], rx[k], phr);
@@ -381,31 +451,34 @@ __device__ __forceinline__ void sg_rls_warp(SgShared &S, const ChainDesc &d, int
 #pragma unroll
     for (int k = 0; k < kMaxRls; k++) if (k < m) phi = fma(rx[k], rph[k], phi);
     phi = fmax(phi, 1e-8);
-    const double Rr = fmax(S0 - S1, 1e-5);
-    const double rnis = rcp_fast(phi + Rr);
-    const double xprev = row > 0 ? rx[row - 1] : 0.0;                // x_new[row] for row > 0
+    const double rnis = rcp_fast(phi + fmax(S0 - S1, 1e-5));
+    const double xprev = (row > 0 && lane < m) ? rx[row - 1] : 0.0;  // x_new[row] for rows 1..m-1
+    double q1 = xprev * w, q2 = xprev * phr;                         // lanes 1..m-1 contribute; lane 0 and lanes >= m carry 0
+    q1 += shfl_xor(q1, 8); q2 += shfl_xor(q2, 8);
+    q1 += shfl_xor(q1, 4); q2 += shfl_xor(q2, 4);
+    q1 += shfl_xor(q1, 2); q2 += shfl_xor(q2, 2);
+    q1 += shfl_xor(q1, 1); q2 += shfl_xor(q2, 1);
+    const double Q1 = shfl_idx(q1, 0), Q2 = shfl_idx(q2, 0);         // sums over lanes 0..15 (m <= 10)
+    const double w_0 = shfl_idx(w, 0), ph_0 = rph[0];
     bar_sync(kBarS2MR, 96);
     const double bp4 = ldd_vol(&S.bp4);
     const double err = bp4 - p_rls;
     const double err2 = err * err;
-    const double mm = c_exp(-gamma * (err2 * rnis));
+    const double mm = exp_neg(-gamma * (err2 * rnis));
     const double al = fma(0.999 - 0.99, mm, 0.99);
     const double denom = rcp_fast(al + phi), inv_al = rcp_fast(al);
-    w = fma(err * denom, phr, w);                                    // w_row += err * denom * ph_row
-    // next prediction: sum_j x_new[j] w_new[j], x_new = [bp4, x_0 .. x_{m-2}]
-    const double xn = row > 0 ? xprev : bp4;
-    double term = lane < m ? xn * w : 0.0;
-    term += shfl_xor(term, 8); term += shfl_xor(term, 4); term += shfl_xor(term, 2); term += shfl_xor(term, 1);
-    p_rls = shfl_idx(term, 0);                                       // lanes 0..15 carry the sum over lanes 0..15 (m <= 10)
+    const double c = err * denom;
+    p_rls = fma(bp4, fma(c, ph_0, w_0), fma(c, Q2, Q1));
     if (lane == 0) S.p_rls = p_rls;
     __threadfence_block();
     if (t + 1 < n) bar_arrive(kBarMR2S, 96);
-    // ---- off the critical path: P, x, S0, S1 ----
-    const double dp = denom * phr;
+    // ---- off the critical path: w, P, x, S0, S1 ----
+    w = fma(c, phr, w);                                              // w_row += err * denom * ph_row
+    // symmetric by construction, as the reference's one-sided update mirrored (rls.cpp:44-52): ph_i * ph_j commutes
 #pragma unroll
-    for (int k = 0; k < kMaxRls; k++) if (k < m) P[k] = (P[k] - dp * rph[k]) * inv_al;
+    for (int k = 0; k < kMaxRls; k++) if (k < m) P[k] = fma(-denom, phr * rph[k], P[k]) * inv_al;
     __syncwarp();                                                    // every lane has read rx / rph
-    if (lane < m) rx[lane] = xn;
+    if (lane < m) rx[lane] = row > 0 ? xprev : bp4;
     __syncwarp();
     S0 = fma(0.95, S0, (1.0 - 0.95) * err2);
     S1 = fma(0.95, S1, (1.0 - 0.95) * phi);
@@ -439,8 +512,10 @@ __device__ __forceinline__ void sg_bias_warp(SgShared &S, const ChainDesc &d, in
         const int b9 = fabs(d0) > 32 ? 0 : 1;
         const int b10 = 2 * h0 - h1 > px ? 0 : 1;
         const int b11 = 3 * h0 - 3 * h1 + h2 > px ? 0 : 1;
-        const double sum = (fabs(d0) + fabs(d1) + fabs(d2) + fabs(d3) + fabs(d4)) * 0.2;
-        mix_ctx = sum > 512 ? 2 : (sum > 32 ? 1 : 0);
+        // bias.h:103-108 compares sum/5 with 32 and 512; the deltas are integers, so sum/5 > 32 <=> sum > 160 exactly
+        // (a multiplication by 0.2 is NOT equivalent: 160 * 0.2 > 32 in binary floating point)
+        const double sum = fabs(d0) + fabs(d1) + fabs(d2) + fabs(d3) + fabs(d4);
+        mix_ctx = sum > 2560 ? 2 : (sum > 160 ? 1 : 0);
         ctx0 = b0 + (b2 << 1) + (b9 << 2) + (b10 << 3) + (b11 << 4);
         ctx1 = b2 + (b3 << 1) + (b4 << 2);
         ctx2 = b5 + (b6 << 1) + (b7 << 2) + (b8 << 3);
@@ -471,7 +546,7 @@ __device__ __forceinline__ void sg_bias_warp(SgShared &S, const ChainDesc &d, in
         const double bv = fmax(0.0, S.bvar), bm = S.bmean;
         const double diff = delta - bm;
         const double z = diff * diff * rcp_fast(bv + 1E-5);
-        const double wgt = c_exp(-0.5 * z);
+        const double wgt = exp_neg(-0.5 * z);
         double hin = 0.0, hdl = 0.0;
         if (lane < 8) { hin = lane > 0 ? S.hist_in[lane - 1] : val; hdl = lane > 0 ? S.hist_d[lane - 1] : delta; }
         __syncwarp();
@@ -507,6 +582,11 @@ __host__ __device__ inline int sg_block_len(int N, int tap_threads)  // taps j =
   if (L < 1) L = 1;
   return L | 1;
 }
+__host__ __device__ inline int sg_padded_taps(int N, int L)          // taps 1..np: whole blocks of L covering 1..N-1
+{
+  const int taps = N - 1 > 0 ? N - 1 : 0;
+  return ((taps + L - 1) / L) * L;
+}
 
 template <class CFG>
 __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_sg_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
@@ -521,11 +601,12 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
     const int regs[kStages] = {CFG::r0, CFG::r1, CFG::r2, CFG::r3};
     for (int s = 0; s < kStages; s++) {
       const int N = d.vn[s];
-      S.L[s] = sg_block_len(N, CFG::tap_threads);
-      S.h[s] = sp; sp += 2 * (N + 2);
-      S.mu[s] = sp; sp += N;
-      S.pw[s] = sp; sp += N;
-      if (S.L[s] > regs[s]) { S.wt[s] = sp; sp += N; } else S.wt[s] = nullptr;
+      const int L = sg_block_len(N, CFG::tap_threads), np = sg_padded_taps(N, L);
+      S.L[s] = L; S.M[s] = np + 3;                                   // ring: h_0 .. h_{np+1} are read, one more slot takes the push
+      S.h[s] = sp; sp += 2 * (np + 3);
+      S.mu[s] = sp; sp += np + 1;
+      S.pw[s] = sp; sp += np + 1;
+      if (L > regs[s]) { S.wt[s] = sp; sp += np + 1; } else S.wt[s] = nullptr;
     }
     S.clamped = 0; S.bad = 0;
   }
@@ -536,15 +617,15 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
   }
   __syncthreads();
   for (int s = 0; s < kStages; s++) {
-    const int N = d.vn[s];
+    const int N = d.vn[s], np = S.M[s] - 3;
     const double md = d.vmudecay[s], pd = d.vpowdecay[s];
     double *h = S.h[s], *mu = S.mu[s], *pw = S.pw[s], *wt = S.wt[s];
-    for (int i = tid; i < N; i += CFG::threads) {
-      pw[i] = 1.0 / c_pow((double)(1 + i), pd);                      // ls.h:39 (the canonical table values)
-      mu[i] = c_pow(md, (double)i);                                  // ls.h:41
+    for (int i = tid; i <= np; i += CFG::threads) {                  // entries beyond the stage's taps are zero: padded taps do nothing
+      pw[i] = i < N ? 1.0 / c_pow((double)(1 + i), pd) : 0.0;        // ls.h:39 (the canonical table values)
+      mu[i] = i < N ? c_pow(md, (double)i) : 0.0;                    // ls.h:41
       if (wt) wt[i] = 0.0;
     }
-    for (int i = tid; i < 2 * (N + 2); i += CFG::threads) h[i] = 0.0;
+    for (int i = tid; i < 2 * (np + 3); i += CFG::threads) h[i] = 0.0;
   }
   __syncthreads();
   if (tid < kStages) {                                               // sum_powtab accumulates sequentially (ls.h:40)
@@ -555,6 +636,7 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
     S.sum_pow[tid] = sp;
   }
   if (tid < 2 * kMixN) S.v[tid / kMixN][tid % kMixN] = 1.0 / kMixN;
+  if (tid < kMixN) S.wi[tid] = 1.0 / kMixN;                          // max(0.5 * 0.2 + 0.5 * 0.2, 0)
   if (tid < 2) S.sw[tid] = 0.5;
   if (tid < 64) { S.cnt[0][tid] = 4.0; S.cnt[1][tid] = 4.0; S.cnt[2][tid] = 4.0; }
   __syncthreads();
@@ -781,6 +863,169 @@ __global__ void __launch_bounds__(kOT, (NB <= 3 ? 3 : (NB <= 5 ? 2 : 1))) ols_sg
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ols_warp_kernel<NP>: orders n <= NP <= 32, ONE WARP per chain, four independent chains per CTA, no CTA barrier in the loop.
+// Lane i owns row i of the covariance and of the work matrix in REGISTERS (rows n..NP-1 are padding: zero regressors, pivot
+// nu); the right-hand side is a column (one register per lane), so the forward substitution rides along with the
+// elimination. Per column step a lane publishes its entry of column j through a double-buffered shared-memory vector, one
+// __syncwarp, every lane reads the pivot and the column (128-bit broadcast loads) and applies the rank-1 update to its row:
+// ~1 300 instructions per 32 x 32 solve for the whole chain (the block-cyclic kernel above spends ~30 000 over 8 warps).
+// L goes to shared memory by rows for the back substitution.
+struct OlsWarpShared {
+  double xo[kOXW], xq[kOXW];
+  double Xs[kOKB][32];
+  double col[2][36];                                                 // column j at [0, 32), right-hand side of the pivot row at [32]
+  double Ls[32][33];
+};
+
+template <int NP>
+__global__ void __launch_bounds__(128, (NP <= 16 ? 4 : (NP <= 24 ? 3 : 2))) ols_warp_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx, int count)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 4 + wib;
+  if (ci >= count) return;
+  const ChainDesc &d = descs[idx ? idx[ci] : ci];
+  OlsWarpShared &S = reinterpret_cast<OlsWarpShared *>(smem_raw)[wib];
+  const int N = d.n;
+  const int n = d.lenA + d.lenB;
+  const double lambda = d.lambda, nu = d.nu, one_m_lambda = 1.0 - d.lambda;
+  const int lenA = d.lenA, lagB = d.lagB, minB = d.minB, backB = d.backB;
+  double cv[NP], W[NP];
+#pragma unroll
+  for (int c = 0; c < NP; c++) { cv[c] = 0.0; W[c] = 0.0; }
+  double bcv = 0.0, wgt = 0.0, esum = 0.0;
+  int km = 0;
+  for (int q = lane; q < 192; q += 32) {
+    const int ix = q - 64;
+    const bool in = ix >= 0 && ix < N;
+    S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+    S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+  }
+  __syncwarp();
+  int fill_end = 128;
+  int t = 0;
+  while (t < N) {
+    if (fill_end < t + 68) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int ix = fill_end + lane + 32 * h;
+        const bool in = ix < N;
+        S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+        S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+      }
+      fill_end += 64;
+      __syncwarp();
+    }
+    const int kb = min(min(kOKB, d.k - km), N - t);
+    // ---- this lane's regressor element of the block's samples (pred.cpp:17-31), the samples themselves ----
+    double xi[kOKB], val[kOKB];
+#pragma unroll
+    for (int u = 0; u < kOKB; u++) {
+      const int tt = t + u;
+      const int sB = max(tt - lagB, minB) - backB;
+      double v = 0.0;
+      if (u < kb) {
+        if (lane < lenA) v = S.xo[(tt - lenA + lane) & (kOXW - 1)];
+        else if (lane < n) v = S.xq[(sB + lane - lenA) & (kOXW - 1)];
+      }
+      xi[u] = v;
+      val[u] = u < kb ? S.xo[tt & (kOXW - 1)] : 0.0;
+      S.Xs[u][lane] = v;
+    }
+    // ---- predictions (ols.cpp:22-25) ----
+    double pu[kOKB];
+#pragma unroll
+    for (int u = 0; u < kOKB; u++) pu[u] = xi[u] * wgt;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < kOKB; u++) pu[u] += shfl_xor(pu[u], o);
+    }
+    if (lane < kb) d.plpc[t + lane] = lane == 0 ? pu[0] : (lane == 1 ? pu[1] : (lane == 2 ? pu[2] : pu[3]));
+    // ---- IRLS weights (ols.cpp:29-36): lane u computes the power of sample u ----
+    double es_mine = 1.0;
+#pragma unroll
+    for (int u = 0; u < kOKB; u++)
+      if (u < kb) {
+        esum = fma(d.beta_sum, esum, fabs(val[u] - pu[u]));
+        if (lane == u) es_mine = esum;
+      }
+    const double ffl = one_m_lambda * c_pow(es_mine + d.beta_add, -d.beta_pow);
+    // ---- covariance: one rank-kb update of the lane's row and of its right-hand side (ols.cpp:38-45) ----
+    km += kb;
+    const bool solve = km >= d.k;
+    {
+      double fx[kOKB], lamk = 1.0;
+#pragma unroll
+      for (int u = kOKB - 1; u >= 0; u--) {
+        const double f = u < kb ? shfl_idx(ffl, u) * lamk : 0.0;
+        fx[u] = f * xi[u];
+        if (u < kb) lamk *= lambda;
+      }
+      __syncwarp();                                                  // Xs complete
+#pragma unroll
+      for (int c = 0; c < NP; c += 2) {
+        double2 x[kOKB];
+#pragma unroll
+        for (int u = 0; u < kOKB; u++) x[u] = *reinterpret_cast<const double2 *>(&S.Xs[u][c]);
+        double a = cv[c] * lamk, b = cv[c + 1] * lamk;
+#pragma unroll
+        for (int u = 0; u < kOKB; u++) { a = fma(fx[u], x[u].x, a); b = fma(fx[u], x[u].y, b); }
+        cv[c] = a; cv[c + 1] = b;
+      }
+      double bb = bcv * lamk;
+#pragma unroll
+      for (int u = 0; u < kOKB; u++) bb = fma(fx[u], val[u], bb);
+      bcv = bb;
+      __syncwarp();                                                  // Xs may be rewritten by the next block
+    }
+    if (solve) {
+      km = 0;
+#pragma unroll
+      for (int c = 0; c < NP; c++) W[c] = cv[c] + (c == lane ? nu : 0.0);
+      double y = bcv, z = 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        double *cb = S.col[j & 1];
+        cb[lane] = W[j];
+        if (lane == j) cb[32] = y;
+        __syncwarp();
+        const double dj = cb[j], yj = cb[32];
+        if (dj < 1e-12) ok = false;
+        const double inv = rcp_fast(dj);
+        const double lij = W[j] * inv;
+        if (lane == j) z = y * inv;                                  // (D^-1 L^-1 b)_j
+        if (lane > j) { y = fma(-lij, yj, y); S.Ls[lane][j] = lij; }
+        // trailing update of this lane's row: W[i][c] -= l_ij * W[c][j] (entries above the diagonal are never used)
+        int c = j + 1;
+        if (c & 1) { if (c < NP) W[c] = fma(-lij, cb[c], W[c]); c++; }
+#pragma unroll
+        for (; c + 1 < NP; c += 2) {
+          const double2 u = *reinterpret_cast<const double2 *>(&cb[c]);
+          W[c] = fma(-lij, u.x, W[c]);
+          W[c + 1] = fma(-lij, u.y, W[c + 1]);
+        }
+        if (c < NP) W[c] = fma(-lij, cb[c], W[c]);
+      }
+      __syncwarp();
+      // ---- back substitution L^T w = z: columns in descending order, row k of L is contiguous ----
+      double lk = lane < NP - 1 ? S.Ls[NP - 1][lane] : 0.0;
+#pragma unroll
+      for (int k = NP - 1; k >= 1; k--) {
+        const double cur = lk;
+        if (k >= 2) lk = lane < k - 1 ? S.Ls[k - 1][lane] : 0.0;
+        const double zk = shfl_idx(z, k);
+        if (lane < k) z = fma(-cur, zk, z);
+      }
+      if (ok) wgt = z;
+      __syncwarp();
+    }
+    t += kb;
+  }
+}
+
 } // namespace
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -791,15 +1036,28 @@ size_t cascade_sg_smem_bytes(const int *vn, int large)
   const int regs_l[kStages] = {SgLarge::r0, SgLarge::r1, SgLarge::r2, SgLarge::r3};
   size_t doubles = 0;
   for (int s = 0; s < kStages; s++) {
-    const int N = vn[s], L = sg_block_len(N, large ? SgLarge::tap_threads : SgSmall::tap_threads);
-    doubles += 2 * (size_t)(N + 2) + 2 * (size_t)N;
+    const int N = vn[s], L = sg_block_len(N, large ? SgLarge::tap_threads : SgSmall::tap_threads), np = sg_padded_taps(N, L);
+    doubles += 2 * (size_t)(np + 3) + 2 * (size_t)(np + 1);
     if (!large && L > regs_s[s]) return 0;
-    if (large && L > regs_l[s]) doubles += (size_t)N;
+    if (large && L > regs_l[s]) doubles += (size_t)(np + 1);
   }
   return ((sizeof(SgShared) + 15) & ~size_t(15)) + doubles * 8 + 64;
 }
-int ols_sg_class(int n_ols) { const int nb = (n_ols + 1 + 15) / 16; return nb <= 3 ? 3 : (nb <= 5 ? 5 : 7); }
-size_t ols_sg_smem_bytes(int n_ols) { return ((sizeof(OlsSgShared) + 15) & ~size_t(15)) + (size_t)(n_ols * (n_ols - 1) / 2 + 8) * 8; }
+// OLS kernel classes: orders up to 32 run one warp per chain (ols_warp_kernel<16 / 24 / 32>, classes 16 / 24 / 32), larger ones
+// the 256-thread block-cyclic kernel with 3, 5 or 7 blocks of 16 per matrix dimension (classes 3 / 5 / 7)
+int ols_sg_class(int n_ols)
+{
+  if (n_ols <= 16) return 16;
+  if (n_ols <= 24) return 24;
+  if (n_ols <= 32) return 32;
+  const int nb = (n_ols + 1 + 15) / 16;
+  return nb <= 3 ? 3 : (nb <= 5 ? 5 : 7);
+}
+size_t ols_sg_smem_bytes(int n_ols)
+{
+  if (n_ols <= 32) return 4 * sizeof(OlsWarpShared) + 64;
+  return ((sizeof(OlsSgShared) + 15) & ~size_t(15)) + (size_t)(n_ols * (n_ols - 1) / 2 + 8) * 8;
+}
 
 cudaError_t predictor_sg_init_attributes()
 {
@@ -807,6 +1065,9 @@ cudaError_t predictor_sg_init_attributes()
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_warp_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_sg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_sg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(ols_sg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -815,6 +1076,13 @@ cudaError_t predictor_sg_init_attributes()
 cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream)
 {
   if (count <= 0) return cudaSuccess;
+  if (nb_class >= 16) {
+    const int grid = (count + 3) / 4;
+    if (nb_class == 16) ols_warp_kernel<16><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+    else if (nb_class == 24) ols_warp_kernel<24><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+    else ols_warp_kernel<32><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+    return cudaGetLastError();
+  }
   if (nb_class == 3) ols_sg_kernel<3><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
   else if (nb_class == 5) ols_sg_kernel<5><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
   else ols_sg_kernel<7><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);

@@ -28,5 +28,5 @@ for name, X in (("default", Xd), ("heterogeneous", Xh)):
         res[grade] = c
         print(f"{name} grade {grade}: P={P} n={n} wall {dt:.3f}s ols {ms[3]:.1f} ms cascade {ms[0]-ms[3]:.1f} ms bitplane {ms[1]:.1f} ms  clk/sample: ols {ms[3]*1e-3*1.965e9/n:.0f} cascade {(ms[0]-ms[3])*1e-3*1.965e9/n:.0f}", flush=True)
     fin = np.isfinite(res[0]) & np.isfinite(res[1])
-    rel = np.abs(res[1][fin] - res[0][fin]) / res[0][fin]
+    rel = np.abs(res[1][fin] - res[0][fin]) / res[0][fin] if fin.any() else np.array([np.nan])
     print(f"{name}: finite {fin.sum()}/{P}, equal costs {np.mean(res[1][fin] == res[0][fin]):.2f}, max rel diff {rel.max():.2e}, argmin {np.argmin(res[0])} {np.argmin(res[1])}, stats {eng.grade_stats()}", flush=True)

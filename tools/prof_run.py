@@ -11,6 +11,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
 kind = int(sys.argv[3]) if len(sys.argv) > 3 else sb.COST_BITPLANE
 eng = sb.Engine(0)
 eng.set_dedup(0)
+eng.set_grade(int(os.environ.get('SACB_GRADE', '0')))
 vmin, vmax, vdef = sb.base_profile()
 pcm = synth_pcm(2, 2, 3).astype(np.int32)
 planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])
