@@ -167,6 +167,9 @@ int Engine::init(int dev, const Engine *parent)
   }
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
   SACB_CUDA(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+  for (auto &s2 : side) SACB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+  SACB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  for (auto &e : ev_join) SACB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (const char *s = std::getenv("SAC_B200_SMEM_KB")) smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_ENC_SMEM_KB")) enc_smem_bytes = std::clamp(std::atoi(s), 24, 226) * 1024;
   if (const char *s = std::getenv("SAC_B200_OLS_SMEM_KB")) ols_smem_bytes = std::clamp(std::atoi(s), 12, 226) * 1024;
@@ -193,6 +196,9 @@ void Engine::destroy()
   if (!is_helper) bt.destroy();
   for (auto &e : ev) if (e) cudaEventDestroy(e);
   if (ev_wait) cudaEventDestroy(ev_wait);
+  for (auto &s2 : side) if (s2) { cudaStreamSynchronize(s2); cudaStreamDestroy(s2); s2 = nullptr; }
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  for (auto &e : ev_join) if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr;
 }
@@ -329,19 +335,24 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
   // (probe switch SACB_SG_PARTS: bit 0 = search-grade OLS, bit 1 = search-grade cascade; default both)
   static const int sg_parts = [] { const char *v = std::getenv("SACB_SG_PARTS"); return v ? std::atoi(v) : 3; }();
   {
-    const int kOlsClasses = 6;
-    const int cls_id[kOlsClasses] = {16, 24, 32, 3, 5, 7};            // ols_sg_class values, cheapest first
-    std::vector<int> ols_cls[kOlsClasses], casc[3];                   // cascade: small, large, canonical fallback
-    size_t ols_sm[kOlsClasses] = {0, 0, 0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
+    // OLS: orders up to 32 on the one-warp register kernels (classes 16 / 24 / 32), larger ones on the canonical team kernel
+    // (measured: the 256-thread block-cyclic search-grade kernel loses to it, profiles/README.md). Cascade: small (two CTAs per SM),
+    // large (one), canonical fallback for chains whose tables exceed shared memory.
+    const int kOlsClasses = 4;
+    const int cls_id[kOlsClasses] = {16, 24, 32, 0};                  // 0: canonical ols_kernel
+    std::vector<int> ols_cls[kOlsClasses], casc[3];
+    size_t ols_sm[kOlsClasses] = {0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
+    size_t need_w2 = 0, need_both2 = 0;
     for (int v = 0; v < nv; v++) {
       const int u = ols_rep[v];
       const int n = ols_order(hps[slot_job[u]], slot_cc[u]);
-      const int id = ols_sg_class(n);
-      int c = 0;
-      while (cls_id[c] != id) c++;
+      const int c = n <= 16 ? 0 : (n <= 24 ? 1 : (n <= 32 ? 2 : 3));
       ols_cls[c].push_back(nu + v);
-      ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
+      if (c < 3) ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
+      else { const size_t ld = ((size_t)n + 1) | 1, mat = ((size_t)n + 1) * ld * 8; need_w2 = std::max(need_w2, mat); need_both2 = std::max(need_both2, 2 * mat); }
     }
+    if (!ols_cls[3].empty())
+      ols_sm[3] = std::max<size_t>(std::max<size_t>(std::min(ols_head + need_both2, ols_cap), std::min<size_t>(ols_head + need_w2, 200 * 1024)), (size_t)ols_smem_bytes);
     const size_t kSmallCap = 112 * 1024, kLargeCap = 226 * 1024;     // two CTAs per SM / one
     for (int u = 0; u < nu; u++) {
       const int *vn = hps[slot_job[u]].vn[slot_cc[u]];
@@ -360,19 +371,45 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     for (int c = 0; c < kOlsClasses; c++) { ooff[c] = off; for (int x : ols_cls[c]) h_idx.p[off++] = x; }
     for (int c = 0; c < 3; c++) { coff[c] = off; for (int x : casc[c]) h_idx.p[off++] = x; }
     SACB_CUDA(cudaMemcpyAsync(d_idx.p, h_idx.p, sizeof(int) * off, cudaMemcpyHostToDevice, stream));
-    if (!(sg_parts & 1)) {                                          // canonical OLS kernel over all stages
-      SACB_CUDA(launch_predictor_enc(d_descs.p + nu, nv, d_descs.p, 0, casc_smem, ols_smem, stream, nullptr));
+    // fork: the classes run side by side (a launch ends with its slowest chain; serialised they would add up)
+    int used = 0;
+    auto fork_stream = [&](int k) -> cudaStream_t { return k == 0 ? stream : side[(k - 1) % kSide]; };
+    auto join_all = [&]() -> int {
+      for (int k = 1; k < used && k <= kSide; k++) {
+        SACB_CUDA(cudaEventRecord(ev_join[k - 1], side[k - 1]));
+        SACB_CUDA(cudaStreamWaitEvent(stream, ev_join[k - 1], 0));
+      }
+      used = 0;
+      return SAC_OK;
+    };
+    auto next_stream = [&](cudaStream_t &out) -> int {
+      const int k = used++;
+      out = fork_stream(k);
+      if (k >= 1 && k <= kSide) SACB_CUDA(cudaStreamWaitEvent(out, ev_fork, 0));
+      return SAC_OK;
+    };
+    SACB_CUDA(cudaEventRecord(ev_fork, stream));
+    if (!(sg_parts & 1)) { ols_cls[3].clear(); for (int v = 0; v < nv; v++) ols_cls[3].push_back(nu + v); }
+    for (int c = kOlsClasses - 1; c >= 0; c--) {                    // the longest-running class first, on the main stream
+      if (ols_cls[c].empty() || (!(sg_parts & 1) && c < 3)) continue;
+      cudaStream_t s2; int rc2 = next_stream(s2); if (rc2) return rc2;
+      if (c == 3) {
+        if (!(sg_parts & 1)) SACB_CUDA(launch_ols_canonical(d_descs.p + nu, nullptr, nv, ols_smem, s2));
+        else SACB_CUDA(launch_ols_canonical(d_descs.p, d_idx.p + ooff[3], (int)ols_cls[3].size(), (int)ols_sm[3], s2));
+      } else SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_id[c], (int)ols_sm[c], s2));
       launches++; last_launches[0]++;
     }
-    for (int c = kOlsClasses - 1; c >= 0 && (sg_parts & 1); c--)    // the longest-running class first
-      if (!ols_cls[c].empty()) {
-        SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_id[c], (int)ols_sm[c], stream));
-        launches++; last_launches[0]++;
-      }
+    { int rc2 = join_all(); if (rc2) return rc2; }
     SACB_CUDA(cudaEventRecord(ev[4], stream));
-    if (!casc[2].empty()) { SACB_CUDA(launch_cascade_canonical(d_descs.p, d_idx.p + coff[2], (int)casc[2].size(), (int)casc_sm[2], stream)); launches++; last_launches[0]++; }
-    if (!casc[1].empty()) { SACB_CUDA(launch_cascade_sg(d_descs.p, d_idx.p + coff[1], (int)casc[1].size(), 1, (int)casc_sm[1], stream)); launches++; last_launches[0]++; }
-    if (!casc[0].empty()) { SACB_CUDA(launch_cascade_sg(d_descs.p, d_idx.p + coff[0], (int)casc[0].size(), 0, (int)casc_sm[0], stream)); launches++; last_launches[0]++; }
+    SACB_CUDA(cudaEventRecord(ev_fork, stream));
+    for (int c = 2; c >= 0; c--) {
+      if (casc[c].empty()) continue;
+      cudaStream_t s2; int rc2 = next_stream(s2); if (rc2) return rc2;
+      if (c == 2) SACB_CUDA(launch_cascade_canonical(d_descs.p, d_idx.p + coff[2], (int)casc[2].size(), (int)casc_sm[2], s2));
+      else SACB_CUDA(launch_cascade_sg(d_descs.p, d_idx.p + coff[c], (int)casc[c].size(), c, (int)casc_sm[c], s2));
+      launches++; last_launches[0]++;
+    }
+    { int rc2 = join_all(); if (rc2) return rc2; }
     SACB_CUDA(cudaEventRecord(ev[1], stream));
   }
   return SAC_OK;

@@ -80,6 +80,10 @@ struct Engine {           // sac_engine
   double total_ms[4] = {0, 0, 0, 0};         // since creation, CUDA events on this engine's stream: ols, cascade, bitplane, other cost kernels
   long long total_calls = 0;                 // population evaluations timed into total_ms
   bool ev4_recorded = false;                 // ev[4] (between OLS and cascade) belongs to the call being timed
+  // side streams: the kernel classes of one evaluation (OLS by order, cascade by size) run side by side, fork / join by events
+  enum { kSide = 3 };
+  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
   long long last_launches[4] = {0, 0, 0, 0};
 
   DevBuf<ChainDesc> d_descs;
@@ -149,6 +153,7 @@ size_t predictor_ols_shared_bytes();
 long long predictor_enc_smem_doubles(const int *vn);
 cudaError_t predictor_enc_init_attributes();
 cudaError_t launch_cascade_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream);
+cudaError_t launch_ols_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream);
 // search-grade kernels (predictor_sg.cu)
 cudaError_t predictor_sg_init_attributes();
 size_t cascade_sg_smem_bytes(const int *vn, int large);          // 0: the chain does not fit that variant

@@ -873,10 +873,10 @@ __device__ __forceinline__ void ols_team(OlsShared &S, const ChainDesc &d, int t
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTeam, 5) ols_kernel(const ChainDesc *__restrict__ descs)
+__global__ void __launch_bounds__(kTeam, 5) ols_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ChainDesc &d = descs[blockIdx.x];
+  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
   OlsShared &S = *reinterpret_cast<OlsShared *>(smem_raw);
   const int tid = threadIdx.x;
   const int n_ols = d.lenA + d.lenB;
@@ -1020,7 +1020,7 @@ cudaError_t predictor_enc_init_attributes()
 cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const ChainDesc *d_descs, int nchains, int smem_bytes,
                                  int ols_smem_bytes, cudaStream_t stream, cudaEvent_t between)
 {
-  ols_kernel<<<nols, kTeam, ols_smem_bytes, stream>>>(d_ols_descs);
+  ols_kernel<<<nols, kTeam, ols_smem_bytes, stream>>>(d_ols_descs, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess) return e;
@@ -1028,7 +1028,13 @@ cudaError_t launch_predictor_enc(const ChainDesc *d_ols_descs, int nols, const C
   cascade_kernel<<<nchains, kEncThreads, smem_bytes, stream>>>(d_descs, nullptr);
   return cudaGetLastError();
 }
-// the cascade alone over a subset of the descriptors (chains the search-grade kernels do not take)
+// the OLS stages / the cascade alone over a subset of the descriptors (chains the search-grade kernels do not take)
+cudaError_t launch_ols_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream)
+{
+  if (count <= 0) return cudaSuccess;
+  ols_kernel<<<count, kTeam, smem_bytes, stream>>>(d_descs, d_idx);
+  return cudaGetLastError();
+}
 cudaError_t launch_cascade_canonical(const ChainDesc *d_descs, const int *d_idx, int count, int smem_bytes, cudaStream_t stream)
 {
   if (count <= 0) return cudaSuccess;

@@ -1038,8 +1038,7 @@ size_t cascade_sg_smem_bytes(const int *vn, int large)
   for (int s = 0; s < kStages; s++) {
     const int N = vn[s], L = sg_block_len(N, large ? SgLarge::tap_threads : SgSmall::tap_threads), np = sg_padded_taps(N, L);
     doubles += 2 * (size_t)(np + 3) + 2 * (size_t)(np + 1);
-    if (!large && L > regs_s[s]) return 0;
-    if (large && L > regs_l[s]) doubles += (size_t)(np + 1);
+    if (L > (large ? regs_l[s] : regs_s[s])) doubles += (size_t)(np + 1);   // blocks longer than the register slots keep the rest of their weights here
   }
   return ((sizeof(SgShared) + 15) & ~size_t(15)) + doubles * 8 + 64;
 }

@@ -58,7 +58,9 @@ def test_search_grade_residuals_equal_canonical_up_to_rounding_flips(engine):
     planes, means, mm = ol.analyse([pcm[:, 0], pcm[:, 1]])
     win = engine.window(planes, mm)
     big = vdef.copy(); big[28] = 6000; big[29] = 1500; big[31] = 3000; big[32] = 900; big[33] = 700; big[38] = 300; big[24] = 30; big[9] = 20; big[25] = 32; big[26] = 30; big[27] = 31
-    huge = vmax.copy()                                              # tables beyond shared memory: canonical cascade fallback
+    huge = vdef.copy()                                              # tables beyond shared memory: canonical cascade fallback
+    for i, v in ((28, 8192), (29, 4096), (30, 2048), (37, 1024), (31, 8000), (32, 4000), (33, 2000), (38, 1000)):
+        huge[i] = v
     small = vmin.copy()
     swapped = random_profile(rng, vmin, vmax); swapped[27] = -5.0
     profs = [vdef, big, huge, small, swapped] + [random_profile(rng, vmin, vmax, cap0=None, cap1=None) for _ in range(6)]
