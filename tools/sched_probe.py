@@ -26,13 +26,13 @@ cfg = sb.make_cfg("best", num_threads=width if mode == "gen" else 0, spec=width,
                   inflight=inflight, reset=1, grade=grade)
 warm = sb.make_cfg("best", num_threads=0, spec=4, maxnfunc=3, frame_parallel=2, inflight=inflight, reset=1, grade=grade)
 eng.frames_encode(warm, frames[:min(nframes, inflight)], FRAME)          # pools, helper engines
-d0 = eng.dedup_totals(); l0 = eng.launches
+d0 = eng.dedup_totals(); l0 = eng.launches; tm0, c0 = eng.total_timing(); g0 = eng.grade_stats()
 t0 = time.perf_counter()
 rec, _ = eng.frames_encode(cfg, frames, FRAME)
 dt = time.perf_counter() - t0
-d1 = eng.dedup_totals()
+d1 = eng.dedup_totals(); tm1, c1 = eng.total_timing(); g1 = eng.grade_stats()
 print(json.dumps({"mode": mode, "width": width, "inflight": inflight, "frames": nframes, "nfunc": nfunc, "grade": grade, "seconds": round(dt, 2),
                   "candidates": (d1[0] - d0[0]) // 2, "chains_evaluated": d1[1] - d0[1], "ols_evaluated": d1[2] - d0[2],
                   "candidates_per_s": round((d1[0] - d0[0]) / 2 / dt, 2), "s_per_frame": round(dt / nframes, 2), "launches": eng.launches - l0,
-                  "bytes": int(len(rec)), "lpt": os.environ.get("SACB_LPT", "0"), "lib": os.path.basename(sb.LIB_PATH)}), flush=True)
+                  "bytes": int(len(rec)), "device_ms": [round(a - b, 1) for a, b in zip(tm1, tm0)], "evaluations": c1 - c0, "grade_stats": [a - b for a, b in zip(g1, g0)], "lpt": os.environ.get("SACB_LPT", "0"), "lib": os.path.basename(sb.LIB_PATH)}), flush=True)
 eng.close()
