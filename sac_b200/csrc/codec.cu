@@ -129,7 +129,7 @@ void DdsSearch::consume(const double *costs)
       if (ok) { xb_ = pending_[i]; fb_ = costs[i]; }
       ssc0_step(ok);
       nfunc_ = sp.nfunc + 1;
-      q_est_ = 0.95 * q_est_ + 0.05 * (ok ? 1.0 : 0.0);
+      q_est_ = std::clamp(0.97 * q_est_ + 0.03 * (ok ? 1.0 : 0.0), 0.03, 0.5);
       if (ok) { eng_ = sp.rng_after; break; }                           // later candidates were drawn around the old incumbent
     }
     return;
@@ -820,6 +820,7 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
         const int nopt = std::min(fw[f].n, (int)std::ceil(max_framesize * cfg.fraction));   // libsac.cpp:367-368
         wn.push_back(nopt); wfrom.push_back((fw[f].n - nopt) / 2);
       }
+      const auto t_search0 = std::chrono::steady_clock::now();
       while (true) {
         std::vector<const sac_window *> wins;
         std::vector<int> from, nn, owner;
@@ -847,7 +848,8 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
           ss[si]->consume(&cost[off]);
           off += cands[si].size();
           if (cfg.verbose > 1)
-            std::fprintf(stderr, "  frame %d DDS %5d: %0.4f s=%0.3f\n", f0 + (int)si, ss[si]->nfunc(), ss[si]->best_cost(), ss[si]->sigma());
+            std::fprintf(stderr, "  frame %d DDS %5d: %0.4f s=%0.3f  batch %d  t=%.2fs\n", f0 + (int)si, ss[si]->nfunc(), ss[si]->best_cost(), ss[si]->sigma(),
+                         (int)cands[si].size(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t_search0).count());
         }
       }
       if (const char *tp = std::getenv("SACB_TRACE_DDS")) {           // probe: the steps of the sequential search, one line each

@@ -59,7 +59,7 @@ private:
   struct SpecPoint { double sigma; int nsucc, nfail, nfunc; std::mt19937 rng_after; };
   std::vector<SpecPoint> spec_pts_;
   int spec_ = 1;
-  double q_est_ = 0.5;                        // running estimate of the per-step success rate (sizes the batches)
+  double q_est_ = 0.125;                      // running estimate of the per-step success rate (sizes the batches); typical: 0.07 .. 0.15
   long long evaluated_ = 0;
   bool trace_on_ = false;
   std::vector<std::pair<double, std::vector<double>>> trace_;
