@@ -838,9 +838,12 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
           }
         }
         if (wins.empty()) break;
-        std::vector<double> cost(wins.size());
+        std::vector<double> cost(wins.size()), thr(wins.size());
+        for (size_t j = 0; j < wins.size(); j++) thr[j] = ss[owner[j]]->accept_below();
+        e->redo_below = thr.data();
         int rc = sac_eval_jobs(reinterpret_cast<sac_engine *>(e), (int)wins.size(), wins.data(), from.data(), nn.data(), bases.data(),
                                dims.data(), D, X.data(), cfg.cost_kind, cfg.optk, cost.data());
+        e->redo_below = nullptr;
         if (rc) return rc;
         size_t off = 0;
         for (size_t si = 0; si < ss.size(); si++) {

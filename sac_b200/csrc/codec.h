@@ -2,6 +2,7 @@
 #ifndef SAC_B200_CODEC_H
 #define SAC_B200_CODEC_H
 #include <cstdint>
+#include <limits>
 #include <random>
 #include <string>
 #include <utility>
@@ -22,6 +23,8 @@ public:
   virtual double best_cost() const = 0;
   virtual double sigma() const = 0;
   virtual int nfunc() const = 0;
+  // a candidate can only change the search if its cost is below this (+inf while no cost is known)
+  virtual double accept_below() const { return std::numeric_limits<double>::infinity(); }
 };
 
 // DDS (OptDDS::run_single / run_mt, /root/reference src/opt/dds.cpp:33-106)
@@ -31,10 +34,11 @@ public:
   DdsSearch(int D, const double *xmin, const double *xmax, const double *xstart, int nfunc_max, int num_threads, double sigma_init,
             int spec = 1);
   bool done() const override { return started_ && nfunc_ >= nfunc_max_; }
-  long long evaluated() const { return evaluated_; }
+  double accept_below() const override { return started_ ? fb_ : std::numeric_limits<double>::infinity(); }
+  long long evaluated() const { return evaluated_; }   // candidates handed out so far (>= nfunc() when speculating)
   // every step of the sequential search as (candidate, cost), in order -- recorded when trace(true) was called (probes)
   void trace(bool on) { trace_on_ = on; }
-  const std::vector<std::pair<double, std::vector<double>>> &traced() const { return trace_; }   // candidates handed out so far (>= nfunc() when speculating)
+  const std::vector<std::pair<double, std::vector<double>>> &traced() const { return trace_; }
   void propose(std::vector<std::vector<double>> &cands) override;
   void consume(const double *costs) override;
   const std::vector<double> &best_x() const override { return xb_; }

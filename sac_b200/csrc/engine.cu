@@ -737,8 +737,15 @@ int sac_eval_jobs(sac_engine *h, int njobs, const sac_window *const *wins, const
   if (rc) return rc;
   if (e->grade) {
     // chains whose look-ahead met the +-10 weight clamp are not search-grade exact: those jobs go through the canonical kernels
+    // ... those that could be accepted, that is: a candidate whose weights run into the clamp is almost always a poor one, and a
+    // cost at or above the search's incumbent is a failure whatever its exact value
     std::vector<int> redo;
-    for (int j = 0; j < njobs; j++) if (e->job_inexact[j]) redo.push_back(j);
+    for (int j = 0; j < njobs; j++) {
+      if (!e->job_inexact[j]) continue;
+      const int orig = order.empty() ? j : order[j];
+      if (e->redo_below && cdst[j] >= e->redo_below[orig]) continue;
+      redo.push_back(j);
+    }
     if (!redo.empty()) {
       e->sg_stats[3] += (long long)redo.size();
       std::vector<Job> rj;

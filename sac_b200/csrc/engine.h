@@ -124,6 +124,8 @@ struct Engine {           // sac_engine
   int grade = 0;
   DevBuf<int> d_idx;              // descriptor indices per kernel class (search-grade launches)
   PinBuf<int> h_idx;
+  const double *redo_below = nullptr;   // set by the search driver around sac_eval_jobs: per job, the cost below which an inexact (clamp-flagged)
+                                        // search-grade result matters -- only those jobs are re-evaluated canonically; null: all of them
   std::vector<char> job_inexact;  // per job of the last run_cost: a chain hit the weight clamp under look-ahead (re-evaluate canonically)
   long long sg_stats[4] = {0, 0, 0, 0};   // chains through cascade_sg small / large / canonical fallback, jobs re-evaluated after a clamp
 

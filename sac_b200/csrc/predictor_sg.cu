@@ -169,11 +169,15 @@ __device__ __forceinline__ void tap_block(double (&w)[R], uint32_t ah, uint32_t 
 // one stage of one tap thread for one sample. hw = shared address of h_0(t); tables at amu0 / apw0 / awt0 (index 0); this
 // thread's block starts at tap j0 and has L taps (odd, uniform over the CTA), the first R of them in registers.
 template <int R>
-__device__ __forceinline__ void tap_stage(double (&w)[R], uint32_t hw, uint32_t amu0, uint32_t apw0, uint32_t awt0, int j0, int L, double gprev,
-                                          double &aB, double &aA, double &aP, bool &clamped)
+__device__ __forceinline__ void tap_stage(double (&w)[R], uint32_t hring, int pos, int M, uint32_t amu0, uint32_t apw0, uint32_t awt0, int j0, int L,
+                                          double gprev, double &aB, double &aA, double &aP, bool &clamped)
 {
+  // the ring keeps its first L + 2 slots a second time behind its end: the L + 2 entries h_{j0-1} .. h_{j0+L} of this block are
+  // contiguous from slot (pos + j0 - 1) mod M whatever the ring position
+  int start = pos + j0 - 1;
+  start -= start >= M ? M : 0;
   const uint32_t o0 = 8u * (uint32_t)j0;
-  const uint32_t ah = hw + o0, amu = amu0 + o0, apw = apw0 + o0;
+  const uint32_t ah = hring + 8u * (uint32_t)(start + 1), amu = amu0 + o0, apw = apw0 + o0;
   switch (L < R ? L : R) {                                           // uniform branch; odd lengths only (sg_block_len)
     case 1: tap_block<R, 1>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
     case 3: if constexpr (R >= 3) tap_block<R, 3>(w, ah, amu, apw, gprev, aB, aA, aP, clamped); break;
@@ -275,11 +279,11 @@ __device__ __forceinline__ void sg_tap_warps(SgShared &S, const ChainDesc &d, in
       double acc[12];
 #pragma unroll
       for (int q = 0; q < 12; q++) acc[q] = 0.0;
-      if (mine[0]) tap_stage<CFG::r0>(w0, ah[0] + 8u * (uint32_t)pos[0], amu[0], apw[0], awt[0], j0[0], L[0], ldd_vol(gp), acc[0], acc[1], acc[2], clamped);
-      if (mine[1]) tap_stage<CFG::r1>(w1, ah[1] + 8u * (uint32_t)pos[1], amu[1], apw[1], awt[1], j0[1], L[1], ldd_vol(gp + 1), acc[3], acc[4], acc[5], clamped);
+      if (mine[0]) tap_stage<CFG::r0>(w0, ah[0], pos[0], M[0], amu[0], apw[0], awt[0], j0[0], L[0], ldd_vol(gp), acc[0], acc[1], acc[2], clamped);
+      if (mine[1]) tap_stage<CFG::r1>(w1, ah[1], pos[1], M[1], amu[1], apw[1], awt[1], j0[1], L[1], ldd_vol(gp + 1), acc[3], acc[4], acc[5], clamped);
       if (wide) {
-        if (mine[2]) tap_stage<CFG::r2>(w2, ah[2] + 8u * (uint32_t)pos[2], amu[2], apw[2], awt[2], j0[2], L[2], ldd_vol(gp + 2), acc[6], acc[7], acc[8], clamped);
-        if (mine[3]) tap_stage<CFG::r3>(w3, ah[3] + 8u * (uint32_t)pos[3], amu[3], apw[3], awt[3], j0[3], L[3], ldd_vol(gp + 3), acc[9], acc[10], acc[11], clamped);
+        if (mine[2]) tap_stage<CFG::r2>(w2, ah[2], pos[2], M[2], amu[2], apw[2], awt[2], j0[2], L[2], ldd_vol(gp + 2), acc[6], acc[7], acc[8], clamped);
+        if (mine[3]) tap_stage<CFG::r3>(w3, ah[3], pos[3], M[3], amu[3], apw[3], awt[3], j0[3], L[3], ldd_vol(gp + 3), acc[9], acc[10], acc[11], clamped);
         warp_sums<16>(acc, 0, lane, &S.sums[t & 1][tw][0]);
       } else {
         warp_sums<8>(acc, 0, lane, &S.sums[t & 1][tw][0]);             // slots 6..11 of this warp stay zero
@@ -300,7 +304,7 @@ __device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, 
   const double alpha = d.proj_alpha, one_m_alpha = 1.0 - d.proj_alpha;
   const int li = lane & 3;                                           // lanes >= 4 shadow lanes 0..3 (results unused)
   const bool own = lane < kStages;
-  const int myM = S.M[li];
+  const int myM = S.M[li], myE = S.L[li] + 2;                        // ring length, slots repeated behind its end
   double *myh = S.h[li];
   const double my_mu = d.vmu[li], my_sp = S.sum_pow[li];
   const double clo = d.casc_lo, chi = d.casc_hi;
@@ -379,7 +383,8 @@ __device__ __forceinline__ void sg_scalar_warp(SgShared &S, const ChainDesc &d, 
       if (own) {
         S.g[t & 1][lane] = g;
         const int np = pos == 0 ? myM - 1 : pos - 1;
-        myh[np] = bpl; myh[np + myM] = bpl;                          // mirrored ring: the window h + pos is always contiguous
+        myh[np] = bpl;
+        if (np < myE) myh[np + myM] = bpl;                           // the first L + 2 slots are kept twice (see tap_stage)
         pos = np;
       }
       if (lane == 16) S.pxq[t & 1] = p_lpc + p_lms;
@@ -603,7 +608,7 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
       const int N = d.vn[s];
       const int L = sg_block_len(N, CFG::tap_threads), np = sg_padded_taps(N, L);
       S.L[s] = L; S.M[s] = np + 3;                                   // ring: h_0 .. h_{np+1} are read, one more slot takes the push
-      S.h[s] = sp; sp += 2 * (np + 3);
+      S.h[s] = sp; sp += (np + 3) + (L + 2);
       S.mu[s] = sp; sp += np + 1;
       S.pw[s] = sp; sp += np + 1;
       if (L > regs[s]) { S.wt[s] = sp; sp += np + 1; } else S.wt[s] = nullptr;
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
       mu[i] = i < N ? c_pow(md, (double)i) : 0.0;                    // ls.h:41
       if (wt) wt[i] = 0.0;
     }
-    for (int i = tid; i < 2 * (np + 3); i += CFG::threads) h[i] = 0.0;
+    for (int i = tid; i < (np + 3) + (S.L[s] + 2); i += CFG::threads) h[i] = 0.0;
   }
   __syncthreads();
   if (tid < kStages) {                                               // sum_powtab accumulates sequentially (ls.h:40)
@@ -1037,7 +1042,7 @@ size_t cascade_sg_smem_bytes(const int *vn, int large)
   size_t doubles = 0;
   for (int s = 0; s < kStages; s++) {
     const int N = vn[s], L = sg_block_len(N, large ? SgLarge::tap_threads : SgSmall::tap_threads), np = sg_padded_taps(N, L);
-    doubles += 2 * (size_t)(np + 3) + 2 * (size_t)(np + 1);
+    doubles += (size_t)(np + 3) + (size_t)(L + 2) + 2 * (size_t)(np + 1);
     if (L > (large ? regs_l[s] : regs_s[s])) doubles += (size_t)(np + 1);   // blocks longer than the register slots keep the rest of their weights here
   }
   return ((sizeof(SgShared) + 15) & ~size_t(15)) + doubles * 8 + 64;
