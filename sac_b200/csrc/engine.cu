@@ -167,6 +167,19 @@ int Engine::init(int dev, const Engine *parent)
   }
   for (auto &e : ev) SACB_CUDA(cudaEventCreate(&e));
   SACB_CUDA(cudaEventCreateWithFlags(&ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+  {
+    // pools allocate stream-ordered on this engine's stream; freed blocks stay in the device's pool (no trim to the OS)
+    static std::once_flag once_pool[64];
+    std::call_once(once_pool[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    });
+    d_descs.s = d_scratch.s = d_scratch_ols.s = d_plpc.s = d_resid.s = d_sums.s = d_flags.s = d_bpjobs.s = d_csig0.s = d_hist.s = d_cost.s = d_bytes.s =
+        d_sparse.s = d_idx.s = stream;
+  }
   for (auto &s2 : side) SACB_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
   SACB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   for (auto &e : ev_join) SACB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -626,13 +639,13 @@ sac_window *sac_window_create(sac_engine *h, int nch, const int32_t *const *plan
   if (!e || nch < 1 || nch > 2 || numsamples <= 0 || !planes || !minmax) { set_error("sac_window_create: bad argument"); return nullptr; }
   cudaSetDevice(e->device);
   Window *w = new Window();
-  w->eng = e; w->device = e->device; w->nch = nch; w->numsamples = numsamples;
+  w->eng = e; w->device = e->device; w->stream = e->stream; w->nch = nch; w->numsamples = numsamples;
   w->d_planes[0] = w->d_planes[1] = nullptr;
   for (int i = 0; i < 2 * nch; i++) w->minmax[i] = minmax[i];
   if (nch == 1) { w->minmax[2] = minmax[0]; w->minmax[3] = minmax[1]; }
   if (e->h_stage.reserve(numsamples) != cudaSuccess) { delete w; set_error("pinned staging allocation failed"); return nullptr; }
   for (int ch = 0; ch < nch; ch++) {
-    if (cudaMalloc(&w->d_planes[ch], sizeof(int32_t) * (size_t)numsamples) != cudaSuccess) { set_error("HBM allocation failed"); sac_window_destroy(reinterpret_cast<sac_window *>(w)); return nullptr; }
+    if (cudaMallocAsync(reinterpret_cast<void **>(&w->d_planes[ch]), sizeof(int32_t) * (size_t)numsamples, e->stream) != cudaSuccess) { set_error("HBM allocation failed"); sac_window_destroy(reinterpret_cast<sac_window *>(w)); return nullptr; }
     std::memcpy(e->h_stage.p, planes[ch], sizeof(int32_t) * (size_t)numsamples);
     cudaMemcpyAsync(w->d_planes[ch], e->h_stage.p, sizeof(int32_t) * (size_t)numsamples, cudaMemcpyHostToDevice, e->stream);
     cudaStreamSynchronize(e->stream);
@@ -644,7 +657,9 @@ void sac_window_destroy(sac_window *h)
   Window *w = reinterpret_cast<Window *>(h);
   if (!w) return;
   cudaSetDevice(w->device);
-  for (int ch = 0; ch < 2; ch++) if (w->d_planes[ch]) cudaFree(w->d_planes[ch]);
+  // stream-ordered on the per-thread default stream: every user of the planes has been waited for by the time a window is
+  // destroyed, and -- unlike cudaFree -- this does not synchronise the device under the other frames in flight
+  for (int ch = 0; ch < 2; ch++) if (w->d_planes[ch]) cudaFreeAsync(w->d_planes[ch], cudaStreamPerThread);
   delete w;
 }
 
@@ -802,7 +817,7 @@ int sac_cost(sac_engine *h, int cost_kind, const int32_t *bufs, int count, int n
   e->begin_call();
   SACB_CUDA(cudaSetDevice(e->device));
   // one mono pseudo-window so that run_cost's bookkeeping applies; residuals are uploaded in place of predictor output
-  Window w; w.eng = e; w.device = e->device; w.nch = 1; w.numsamples = n; w.d_planes[0] = w.d_planes[1] = nullptr;
+  Window w; w.eng = e; w.device = e->device; w.stream = e->stream; w.nch = 1; w.numsamples = n; w.d_planes[0] = w.d_planes[1] = nullptr;
   int32_t mn = 0, mx = 0;
   for (size_t i = 0; i < (size_t)count * n; i++) { mn = std::min(mn, bufs[i]); mx = std::max(mx, bufs[i]); }
   const int32_t R = std::max(-(long long)mn, (long long)mx) > 0 ? (int32_t)std::max(-(long long)mn, (long long)mx) : 1;

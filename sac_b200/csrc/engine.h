@@ -6,6 +6,7 @@
 #include "sparse.h"
 #include "sac_b200.h"
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -19,22 +20,26 @@ int cuda_fail(cudaError_t e, const char *what);
     if (e__ != cudaSuccess) return ::sacb::cuda_fail(e__, #call);    \
   } while (0)
 
-// grow-only device buffer
+// Grow-only device buffer, STREAM-ORDERED (cudaMallocAsync / cudaFreeAsync on the owning engine's stream): cudaFree is a
+// device-wide synchronisation, and with ten frames in flight (a host thread, an engine and pools each) every pool that grew
+// and every frame that finished stalled all the others behind the longest kernel on the device (seconds). All users of a
+// buffer are ordered after the engine's stream (side streams fork from it by events), so stream order is sufficient.
 template <class T> struct DevBuf {
   T *p = nullptr;
   size_t cap = 0;
+  cudaStream_t s = nullptr;
   cudaError_t reserve(size_t n)
   {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
     p = nullptr; cap = 0;
-    size_t want = n + n / 8;
-    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-    if (e != cudaSuccess) { want = n; e = cudaMalloc(&p, want * sizeof(T)); }
+    size_t want = n + n / 4;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&p), want * sizeof(T), s);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); want = n; e = cudaMallocAsync(reinterpret_cast<void **>(&p), want * sizeof(T), s); }
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) cudaFreeAsync(p, s); p = nullptr; cap = 0; }
 };
 template <class T> struct PinBuf {
   T *p = nullptr;
@@ -44,8 +49,9 @@ template <class T> struct PinBuf {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(&p, (n + n / 8) * sizeof(T));
-    if (e == cudaSuccess) cap = n + n / 8;
+    const size_t want = std::max<size_t>(2 * n, 4096 / sizeof(T));   // pinned allocations synchronise too: grow rarely
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
@@ -54,6 +60,7 @@ template <class T> struct PinBuf {
 struct Window {           // sac_window
   struct Engine *eng;
   int device;             // kept here: the window may outlive its engine
+  cudaStream_t stream;    // the planes are allocated stream-ordered on the creating engine's stream
   int nch, numsamples;
   int32_t minmax[4];
   int32_t *d_planes[2];   // HBM, mean-free
