@@ -351,21 +351,21 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     // OLS: orders up to 32 on the one-warp register kernels (classes 16 / 24 / 32), larger ones on the canonical team kernel
     // (measured: the 256-thread block-cyclic search-grade kernel loses to it, profiles/README.md). Cascade: small (two CTAs per SM),
     // large (one), canonical fallback for chains whose tables exceed shared memory.
-    const int kOlsClasses = 4;
-    const int cls_id[kOlsClasses] = {16, 24, 32, 0};                  // 0: canonical ols_kernel
+    const int kOlsClasses = 5;
+    const int cls_id[kOlsClasses] = {16, 24, 32, 64, 0};              // ols_sg_class values: one warp per chain (<= 32), two warps (<= 64); 0 = canonical team kernel (orders 65 .. 96)
     std::vector<int> ols_cls[kOlsClasses], casc[3];
-    size_t ols_sm[kOlsClasses] = {0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
+    size_t ols_sm[kOlsClasses] = {0, 0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
     size_t need_w2 = 0, need_both2 = 0;
     for (int v = 0; v < nv; v++) {
       const int u = ols_rep[v];
       const int n = ols_order(hps[slot_job[u]], slot_cc[u]);
-      const int c = n <= 16 ? 0 : (n <= 24 ? 1 : (n <= 32 ? 2 : 3));
+      const int c = n <= 16 ? 0 : (n <= 24 ? 1 : (n <= 32 ? 2 : (n <= 64 ? 3 : 4)));
       ols_cls[c].push_back(nu + v);
-      if (c < 3) ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
+      if (c < 4) ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
       else { const size_t ld = ((size_t)n + 1) | 1, mat = ((size_t)n + 1) * ld * 8; need_w2 = std::max(need_w2, mat); need_both2 = std::max(need_both2, 2 * mat); }
     }
-    if (!ols_cls[3].empty())
-      ols_sm[3] = std::max<size_t>(std::max<size_t>(std::min(ols_head + need_both2, ols_cap), std::min<size_t>(ols_head + need_w2, 200 * 1024)), (size_t)ols_smem_bytes);
+    if (!ols_cls[4].empty())
+      ols_sm[4] = std::max<size_t>(std::max<size_t>(std::min(ols_head + need_both2, ols_cap), std::min<size_t>(ols_head + need_w2, 200 * 1024)), (size_t)ols_smem_bytes);
     const size_t kSmallCap = 112 * 1024, kLargeCap = 226 * 1024;     // two CTAs per SM / one
     for (int u = 0; u < nu; u++) {
       const int *vn = hps[slot_job[u]].vn[slot_cc[u]];
@@ -402,14 +402,16 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
       return SAC_OK;
     };
     SACB_CUDA(cudaEventRecord(ev_fork, stream));
-    if (!(sg_parts & 1)) { ols_cls[3].clear(); for (int v = 0; v < nv; v++) ols_cls[3].push_back(nu + v); }
-    for (int c = kOlsClasses - 1; c >= 0; c--) {                    // the longest-running class first, on the main stream
-      if (ols_cls[c].empty() || (!(sg_parts & 1) && c < 3)) continue;
+    if (!(sg_parts & 1)) {                                          // probe: canonical OLS kernel over all stages
       cudaStream_t s2; int rc2 = next_stream(s2); if (rc2) return rc2;
-      if (c == 3) {
-        if (!(sg_parts & 1)) SACB_CUDA(launch_ols_canonical(d_descs.p + nu, nullptr, nv, ols_smem, s2));
-        else SACB_CUDA(launch_ols_canonical(d_descs.p, d_idx.p + ooff[3], (int)ols_cls[3].size(), (int)ols_sm[3], s2));
-      } else SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_id[c], (int)ols_sm[c], s2));
+      SACB_CUDA(launch_ols_canonical(d_descs.p + nu, nullptr, nv, ols_smem, s2));
+      launches++; last_launches[0]++;
+    }
+    for (int c = kOlsClasses - 1; c >= 0 && (sg_parts & 1); c--) {  // the longest-running class first, on the main stream
+      if (ols_cls[c].empty()) continue;
+      cudaStream_t s2; int rc2 = next_stream(s2); if (rc2) return rc2;
+      if (cls_id[c] == 0) SACB_CUDA(launch_ols_canonical(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), (int)ols_sm[c], s2));
+      else SACB_CUDA(launch_ols_sg(d_descs.p, d_idx.p + ooff[c], (int)ols_cls[c].size(), cls_id[c], (int)ols_sm[c], s2));
       launches++; last_launches[0]++;
     }
     { int rc2 = join_all(); if (rc2) return rc2; }

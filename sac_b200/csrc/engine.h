@@ -88,9 +88,9 @@ struct Engine {           // sac_engine
   long long total_calls = 0;                 // population evaluations timed into total_ms
   bool ev4_recorded = false;                 // ev[4] (between OLS and cascade) belongs to the call being timed
   // side streams: the kernel classes of one evaluation (OLS by order, cascade by size) run side by side, fork / join by events
-  enum { kSide = 3 };
-  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr};
+  enum { kSide = 4 };
+  cudaStream_t side[kSide] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {nullptr, nullptr, nullptr, nullptr};
   long long last_launches[4] = {0, 0, 0, 0};
 
   DevBuf<ChainDesc> d_descs;

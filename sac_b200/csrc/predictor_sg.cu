@@ -1031,6 +1031,207 @@ __global__ void __launch_bounds__(128, (NP <= 16 ? 4 : (NP <= 24 ? 3 : 2))) ols_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// ols_rows_kernel<NW>: orders 33 .. 32 NW (NW = 2, 3), NW warps per chain, thread i owns ROW i of the work matrix in registers
+// (rows n .. 32 NW - 1 are padding), the covariance lives in shared memory (lower triangle, packed by rows) and is updated
+// once per block of k samples. Elimination as in ols_warp_kernel -- a column per step through a double-buffered shared
+// vector -- with a named barrier over the NW warps per step; finished 8-column groups are skipped with one uniform branch
+// each. L goes to shared memory (packed lower triangle) for the back substitution on warp 0.
+template <int NW> struct OlsRowsShared {
+  double xo[kOXW], xq[kOXW];
+  double Xs[kOKB][32 * NW];
+  double col[2][32 * NW + 4];
+  double part[NW][kOKB], pu[kOKB], ff[kOKB];
+  double z[32 * NW], wv[32 * NW];
+};
+__host__ __device__ inline size_t tri_index(int i) { return (size_t)i * (size_t)(i + 1) / 2; }   // row i of a packed lower triangle (diagonal included)
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, (NW == 2 ? 4 : 2)) ols_rows_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
+{
+  constexpr int NR = 32 * NW;                                        // rows = columns held
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
+  OlsRowsShared<NW> &S = *reinterpret_cast<OlsRowsShared<NW> *>(smem_raw);
+  double *cov = reinterpret_cast<double *>(smem_raw + ((sizeof(OlsRowsShared<NW>) + 15) & ~size_t(15)));   // packed lower triangle, NR rows
+  double *Ls = cov + tri_index(NR);                                  // packed strictly-lower triangle: row i at i(i-1)/2
+  const int tid = threadIdx.x, lane = tid & 31, tw = tid >> 5;
+  const int N = d.n;
+  const int n = d.lenA + d.lenB;
+  const double lambda = d.lambda, nu = d.nu, one_m_lambda = 1.0 - d.lambda;
+  const int lenA = d.lenA, lagB = d.lagB, minB = d.minB, backB = d.backB;
+  double *myrow = cov + tri_index(tid);                              // cov[tid][0 .. tid]
+  for (int c = 0; c <= tid; c++) myrow[c] = 0.0;
+  double W[NR];
+#pragma unroll
+  for (int c = 0; c < NR; c++) W[c] = 0.0;
+  double bcv = 0.0, wgt = 0.0, esum = 0.0;
+  int km = 0;
+  for (int q = tid; q < 192; q += NR) {
+    const int ix = q - 64;
+    const bool in = ix >= 0 && ix < N;
+    S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+    S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+  }
+  int fill_end = 128;
+  int t = 0;
+  auto team = [&]() { bar_sync(1, NR); };
+  team();
+  while (t < N) {
+    if (fill_end < t + 68) {
+      if (tid < 64) {
+        const int ix = fill_end + tid;
+        const bool in = ix < N;
+        S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
+        S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
+      }
+      fill_end += 64;
+      team();
+    }
+    const int kb = min(min(kOKB, d.k - km), N - t);
+    double xi[kOKB], val[kOKB];
+#pragma unroll
+    for (int u = 0; u < kOKB; u++) {
+      const int tt = t + u;
+      const int sB = max(tt - lagB, minB) - backB;
+      double v = 0.0;
+      if (u < kb) {
+        if (tid < lenA) v = S.xo[(tt - lenA + tid) & (kOXW - 1)];
+        else if (tid < n) v = S.xq[(sB + tid - lenA) & (kOXW - 1)];
+      }
+      xi[u] = v;
+      val[u] = u < kb ? S.xo[tt & (kOXW - 1)] : 0.0;
+      S.Xs[u][tid] = v;
+    }
+    // ---- predictions: per-warp butterflies, then the NW partial sums ----
+    {
+      double pp[kOKB];
+#pragma unroll
+      for (int u = 0; u < kOKB; u++) pp[u] = xi[u] * wgt;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < kOKB; u++) pp[u] += shfl_xor(pp[u], o);
+      }
+      if (lane < kOKB) S.part[tw][lane] = lane == 0 ? pp[0] : (lane == 1 ? pp[1] : (lane == 2 ? pp[2] : pp[3]));
+    }
+    team();                                                          // Xs and the partial sums are complete
+    double pu[kOKB];
+#pragma unroll
+    for (int u = 0; u < kOKB; u++) {
+      double s = S.part[0][u];
+#pragma unroll
+      for (int w = 1; w < NW; w++) s += S.part[w][u];
+      pu[u] = s;
+    }
+    if (tid < kb) d.plpc[t + tid] = tid == 0 ? pu[0] : (tid == 1 ? pu[1] : (tid == 2 ? pu[2] : pu[3]));
+    // ---- IRLS weights (ols.cpp:29-36): thread u computes the power of sample u ----
+    double es_mine = 1.0;
+#pragma unroll
+    for (int u = 0; u < kOKB; u++)
+      if (u < kb) {
+        esum = fma(d.beta_sum, esum, fabs(val[u] - pu[u]));
+        if (tid == u) es_mine = esum;
+      }
+    if (tid < kOKB) S.ff[tid] = one_m_lambda * c_pow(es_mine + d.beta_add, -d.beta_pow);
+    team();
+    // ---- covariance (ols.cpp:38-45): one rank-kb update of this thread's row (columns 0 .. tid) and right-hand side ----
+    km += kb;
+    const bool solve = km >= d.k;
+    double lamk = 1.0;
+    {
+      double fx[kOKB];
+#pragma unroll
+      for (int u = kOKB - 1; u >= 0; u--) {
+        const double f = u < kb ? S.ff[u] * lamk : 0.0;
+        fx[u] = f * xi[u];
+        if (u < kb) lamk *= lambda;
+      }
+      const int cend = min(tid, n - 1);                              // rows beyond n (and the part right of the diagonal) stay zero
+      for (int c = 0; c <= cend; c++) {
+        double a = myrow[c] * lamk;
+#pragma unroll
+        for (int u = 0; u < kOKB; u++) a = fma(fx[u], S.Xs[u][c], a);
+        myrow[c] = a;
+      }
+      double bb = bcv * lamk;
+#pragma unroll
+      for (int u = 0; u < kOKB; u++) bb = fma(fx[u], val[u], bb);
+      bcv = bb;
+    }
+    if (solve) {
+      km = 0;
+      team();                                                        // every row of the covariance is up to date
+      // this thread's row of C + nu I, FULL row (the part right of the diagonal comes from the other rows' columns)
+#pragma unroll
+      for (int c = 0; c < NR; c++) {
+        double v = 0.0;
+        if (c <= tid) v = myrow[c];
+        else if (c < n && tid < n) v = cov[tri_index(c) + tid];
+        W[c] = v + (c == tid ? nu : 0.0);
+      }
+      double y = bcv, z = 0.0;
+      bool ok = true;
+      double wj = W[0];                                              // this row's entry of the pivot column, picked up during the previous step
+      for (int j = 0; j < n; j++) {
+        double *cb = S.col[j & 1];
+        cb[tid] = wj;
+        if (tid == j) cb[NR] = y;
+        team();
+        const double dj = cb[j], yj = cb[NR];
+        if (dj < 1e-12) ok = false;
+        const double inv = rcp_fast(dj);
+        const double lij = wj * inv;
+        if (tid == j) z = y * inv;
+        if (tid > j) { y = fma(-lij, yj, y); Ls[tri_index(tid - 1) + j] = lij; }
+        const int jn = j + 1, gn = jn >> 3;
+        double wnext = 0.0;
+#pragma unroll
+        for (int g = 0; g < NR / 8; g++)
+          if (8 * g + 7 > j) {                                       // uniform: groups left of the pivot are finished
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+              const double2 u = *reinterpret_cast<const double2 *>(&cb[8 * g + k]);
+              if (8 * g + k > j) W[8 * g + k] = fma(-lij, u.x, W[8 * g + k]);
+              if (8 * g + k + 1 > j) W[8 * g + k + 1] = fma(-lij, u.y, W[8 * g + k + 1]);
+            }
+            if (g == gn) {                                           // uniform: the group of the next pivot column
+              // W[jn] with a runtime jn, as predicated moves (a C++ select chain makes the compiler move W to local memory)
+#pragma unroll
+              for (int k = 0; k < 8; k++)
+                asm("{ .reg .pred p; setp.eq.s32 p, %2, %3; selp.f64 %0, %1, %0, p; }" : "+d"(wnext) : "d"(W[8 * g + k]), "r"(jn), "r"(8 * g + k));
+            }
+          }
+        wj = wnext;
+      }
+      S.z[tid] = z;
+      team();
+      if (tw == 0) {
+        // back substitution L^T w = z on warp 0: slots lane, lane + 32, ...; row k of L is contiguous
+        double zz[NW];
+#pragma unroll
+        for (int s = 0; s < NW; s++) zz[s] = lane + 32 * s < n ? S.z[lane + 32 * s] : 0.0;
+        for (int k = n - 1; k >= 1; k--) {
+          const double *row = Ls + tri_index(k - 1);
+          const int sl = k >> 5;
+          double zk = zz[0];
+#pragma unroll
+          for (int s = 1; s < NW; s++) if (sl == s) zk = zz[s];
+          zk = shfl_idx(zk, k & 31);
+#pragma unroll
+          for (int s = 0; s < NW; s++) if (lane + 32 * s < k) zz[s] = fma(-row[lane + 32 * s], zk, zz[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NW; s++) S.wv[lane + 32 * s] = zz[s];
+      }
+      team();
+      if (ok) wgt = tid < n ? S.wv[tid] : 0.0;
+    }
+    team();                                                          // Xs, part, ff may be rewritten
+    t += kb;
+  }
+}
+
 } // namespace
 
 // ---- host side -------------------------------------------------------------------------------------------------------
@@ -1054,12 +1255,16 @@ int ols_sg_class(int n_ols)
   if (n_ols <= 16) return 16;
   if (n_ols <= 24) return 24;
   if (n_ols <= 32) return 32;
+  if (n_ols <= 64) return 64;
+  if (n_ols <= 96) return 96;
   const int nb = (n_ols + 1 + 15) / 16;
   return nb <= 3 ? 3 : (nb <= 5 ? 5 : 7);
 }
 size_t ols_sg_smem_bytes(int n_ols)
 {
   if (n_ols <= 32) return 4 * sizeof(OlsWarpShared) + 64;
+  if (n_ols <= 64) return ((sizeof(OlsRowsShared<2>) + 15) & ~size_t(15)) + (tri_index(64) + tri_index(63)) * 8 + 64;
+  if (n_ols <= 96) return ((sizeof(OlsRowsShared<3>) + 15) & ~size_t(15)) + (tri_index(96) + tri_index(95)) * 8 + 64;
   return ((sizeof(OlsSgShared) + 15) & ~size_t(15)) + (size_t)(n_ols * (n_ols - 1) / 2 + 8) * 8;
 }
 
@@ -1069,6 +1274,8 @@ cudaError_t predictor_sg_init_attributes()
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(ols_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_warp_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
@@ -1080,6 +1287,8 @@ cudaError_t predictor_sg_init_attributes()
 cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream)
 {
   if (count <= 0) return cudaSuccess;
+  if (nb_class == 64) { ols_rows_kernel<2><<<count, 64, smem_bytes, stream>>>(d_descs, d_idx); return cudaGetLastError(); }
+  if (nb_class == 96) { ols_rows_kernel<3><<<count, 96, smem_bytes, stream>>>(d_descs, d_idx); return cudaGetLastError(); }
   if (nb_class >= 16) {
     const int grid = (count + 3) / 4;
     if (nb_class == 16) ols_warp_kernel<16><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
