@@ -284,7 +284,7 @@ def main():
         return fs, split_records(rec, count)
 
     if args.warmup > 0:
-        run_steps(warm, max(args.warmup, min(inflight, args.steps)), 0)      # also creates one helper engine per frame in flight
+        run_steps(warm, args.warmup, 0)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()

@@ -352,14 +352,18 @@ int Engine::run_predict(const std::vector<Job> &jobs, std::vector<int> &chain_jo
     // (measured: the 256-thread block-cyclic search-grade kernel loses to it, profiles/README.md). Cascade: small (two CTAs per SM),
     // large (one), canonical fallback for chains whose tables exceed shared memory.
     const int kOlsClasses = 5;
-    const int cls_id[kOlsClasses] = {16, 24, 32, 64, 0};              // ols_sg_class values: one warp per chain (<= 32), two warps (<= 64); 0 = canonical team kernel (orders 65 .. 96)
+    // ols_sg_class values: one warp per chain for orders <= 32; 0 = canonical team kernel for larger orders. (A two-warp
+    // rows-in-registers kernel for orders 33..64 exists, ols_rows_kernel<2>, class 64, SACB_OLS_ROWS=1: measured SLOWER than the
+    // canonical kernel on the B200 -- 257 ms against 230 ms for a whole heterogeneous generation, profiles/README.md -- so it is off.)
+    static const bool use_rows = [] { const char *v = std::getenv("SACB_OLS_ROWS"); return v && v[0] == '1'; }();
+    const int cls_id[kOlsClasses] = {16, 24, 32, 64, 0};
     std::vector<int> ols_cls[kOlsClasses], casc[3];
     size_t ols_sm[kOlsClasses] = {0, 0, 0, 0, 0}, casc_sm[3] = {0, 0, 0};
     size_t need_w2 = 0, need_both2 = 0;
     for (int v = 0; v < nv; v++) {
       const int u = ols_rep[v];
       const int n = ols_order(hps[slot_job[u]], slot_cc[u]);
-      const int c = n <= 16 ? 0 : (n <= 24 ? 1 : (n <= 32 ? 2 : (n <= 64 ? 3 : 4)));
+      const int c = n <= 16 ? 0 : (n <= 24 ? 1 : (n <= 32 ? 2 : ((n <= 64 && use_rows) ? 3 : 4)));
       ols_cls[c].push_back(nu + v);
       if (c < 4) ols_sm[c] = std::max(ols_sm[c], ols_sg_smem_bytes(n));
       else { const size_t ld = ((size_t)n + 1) | 1, mat = ((size_t)n + 1) * ld * 8; need_w2 = std::max(need_w2, mat); need_both2 = std::max(need_both2, 2 * mat); }
