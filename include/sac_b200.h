@@ -200,6 +200,17 @@ long long sac_frame_decode(sac_engine *, int nch, const uint8_t *in, long long l
 typedef struct sac_file_stats { long long in_bytes, out_bytes; int numsamples, nch, samplerate, bits, nframes; double seconds; uint8_t md5[16]; int md5_ok; } sac_file_stats;
 int sac_encode_file(sac_engine *, const sac_cfg *, const char *wav_path, const char *sac_path, sac_file_stats *);
 int sac_decode_file(sac_engine *, const char *sac_path, const char *wav_path, sac_file_stats *);
+/* Several GPUs of one box from the C++ host, one engine per device (sac_engine_create(d)), no collective:
+ *   sac_encode_file_multi  ONE file; its frames are dealt round-robin to the engines, each engine's share in flight on its GPU,
+ *                          records concatenated in frame order (libsac.cpp:565-578). Implies --opt-reset semantics (frames are
+ *                          independent searches, cmdline.cpp:193); the bytes equal sac_encode_file's with reset = 1 on one GPU.
+ *   sac_encode_files       a BATCH of files (Codec::EncodeFile per file, libsac.cpp:782-855): every engine takes the next file of a
+ *                          longest-first queue. status[i] (may be null) receives each file's code; returns the first failure.
+ *                          Two inputs that map to the same output path are refused. */
+int sac_encode_file_multi(sac_engine *const *engines, int nengines, const sac_cfg *, const char *wav_path, const char *sac_path,
+                          sac_file_stats *);
+int sac_encode_files(sac_engine *const *engines, int nengines, const sac_cfg *, int nfiles, const char *const *wav_paths,
+                     const char *const *sac_paths, sac_file_stats *stats, int *status);
 /* Frame prologue of one channel (FrameCoder::AnalyseMonoChannel + zero-mean, libsac.cpp:626-651, 452-458), host only:
  * out3 = {mean (0 when !zero_mean), min, max} with min/max taken after the mean is removed -- the block header's fields. */
 int sac_frame_stats(const int32_t *samples, int n, int zero_mean, int32_t *out3);

@@ -107,6 +107,9 @@ def lib():
         L.sac_frame_decode.argtypes = [C.c_void_p, C.c_int, _u8p, C.c_longlong, C.POINTER(_i32p), C.c_int, _intp]
         L.sac_encode_file.argtypes = [C.c_void_p, C.POINTER(Cfg), C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
         L.sac_decode_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
+        L.sac_encode_file_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Cfg), C.c_char_p, C.c_char_p, C.POINTER(FileStats)]
+        L.sac_encode_files.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Cfg), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                       C.POINTER(FileStats), _intp]
         L.sac_encode_memory.argtypes = [C.c_void_p, C.POINTER(Cfg), _u8p, C.c_longlong, _u8p, C.c_longlong,
                                         C.POINTER(C.c_longlong), C.POINTER(FileStats)]
         L.sac_decode_memory.argtypes = [C.c_void_p, _u8p, C.c_longlong, _u8p, C.c_longlong, C.POINTER(C.c_longlong),
@@ -177,6 +180,26 @@ def dds_run_spec(func, xmin, xmax, xstart, nfunc_max, sigma_init=0.2, spec=16):
     best = lib().sac_dds_run_spec(D, _p(xmin, _f64p), _p(xmax, _f64p), _p(xstart, _f64p), nfunc_max, sigma_init, spec, fn, None,
                                   _p(xbest, _f64p), C.byref(ev))
     return best, xbest, int(ev.value)
+
+
+def encode_file_multi(engines, cfg, wav_path, sac_path):
+    """one file on several GPUs (one Engine each): frames dealt round-robin, --opt-reset semantics"""
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    st = FileStats()
+    _chk(lib().sac_encode_file_multi(arr, len(engines), C.byref(cfg), str(wav_path).encode(), str(sac_path).encode(), C.byref(st)), "sac_encode_file_multi")
+    return st
+
+
+def encode_files(engines, cfg, wav_paths, sac_paths):
+    """a batch of files over several GPUs: returns (per-file FileStats, per-file status)"""
+    n = len(wav_paths)
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    wp = (C.c_char_p * n)(*[str(p).encode() for p in wav_paths]); sp = (C.c_char_p * n)(*[str(p).encode() for p in sac_paths])
+    st = (FileStats * max(n, 1))(); status = np.zeros(max(n, 1), np.int32)
+    rc = lib().sac_encode_files(arr, len(engines), C.byref(cfg), n, wp, sp, st, _p(status, _intp))
+    if rc:
+        raise SacError("sac_encode_files failed (%d): %s" % (rc, lib().sac_last_error().decode()))
+    return list(st)[:n], status[:n].tolist()
 
 
 def analyse_subframes(planes, samplerate):

@@ -1193,6 +1193,66 @@ static int encode_image(Engine *e, const sac_cfg &cfg, const uint8_t *wav, size_
   return SAC_OK;
 }
 
+// One file on SEVERAL GPUs of the box, from the C++ host (no collective: frames are independent searches under --opt-reset
+// semantics, which this path implies, and records are concatenated in frame order, libsac.cpp:565-578). Frames are dealt
+// to the engines round-robin; every engine encodes its share with its frames in flight (frame_parallel = 2) on its own
+// host thread. With one engine this is encode_image with reset = 1.
+static int encode_image_multi(Engine *const *engs, int neng, const sac_cfg &cfg_in, const uint8_t *wav, size_t wav_len, std::vector<uint8_t> &out,
+                              sac_file_stats *st)
+{
+  const auto t0 = std::chrono::steady_clock::now();
+  sac_cfg cfg = cfg_in;
+  cfg.reset = 1; cfg.frame_parallel = 2;
+  ContainerPlan cp;
+  int rc = container_plan(cfg, wav, wav_len, out, cp, true);
+  if (rc) return rc;
+  const WavInfo &wi = cp.wi;
+  const int nframes = (int)cp.ns.size();
+  const int used = std::max(1, std::min(neng, nframes));
+  std::vector<std::vector<int>> share(used);
+  for (int f = 0; f < nframes; f++) share[f % used].push_back(f);
+  std::vector<std::vector<uint8_t>> recs(used);
+  std::vector<int> rcs(used, SAC_OK);
+  std::vector<std::string> errs(used);
+  std::vector<std::thread> th;
+  for (int g = 0; g < used; g++)
+    th.emplace_back([&, g]() {
+      Engine *e = engs[g];
+      cudaSetDevice(e->device);
+      const std::vector<int> &fs = share[g];
+      if (fs.empty()) return;
+      std::vector<const int32_t *> ptrs;
+      std::vector<int> ns;
+      for (int f : fs) {
+        for (int ch = 0; ch < wi.nch; ch++) ptrs.push_back(cp.store[(size_t)f * wi.nch + ch].data());
+        ns.push_back(cp.ns[f]);
+      }
+      float prof[kProfileSize];
+      for (int i = 0; i < kProfileSize; i++) prof[i] = kBaseProfile[i][2];
+      rcs[g] = frames_encode(e, cfg, wi.nch, cp.max_framesize, (int)fs.size(), ptrs.data(), ns.data(), prof, recs[g]);
+      if (rcs[g]) errs[g] = sac_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (int g = 0; g < used; g++) if (rcs[g]) { set_error(errs[g]); return rcs[g]; }
+  // frame f is record number f / used of engine f % used: walk the records (u32 numsamples, 58 f32, per channel 18 B header + payload)
+  std::vector<size_t> pos(used, 0);
+  for (int f = 0; f < nframes; f++) {
+    const std::vector<uint8_t> &r = recs[f % used];
+    size_t p = pos[f % used], q = p + 4 + 4 * (size_t)kProfileSize;
+    for (int ch = 0; ch < wi.nch; ch++) { if (q + 18 > r.size()) { set_error("internal: short frame record"); return SAC_E_FORMAT; } q += 18 + (size_t)get32(r.data() + q); }
+    if (q > r.size()) { set_error("internal: short frame record"); return SAC_E_FORMAT; }
+    out.insert(out.end(), r.begin() + (long)p, r.begin() + (long)q);
+    pos[f % used] = q;
+  }
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->in_bytes = (long long)wav_len; st->out_bytes = (long long)out.size(); st->numsamples = (int)wi.numsamples; st->nch = wi.nch;
+    st->samplerate = wi.samplerate; st->bits = wi.bits; st->nframes = nframes; std::memcpy(st->md5, cp.md5, 16); st->md5_ok = 1;
+    st->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return SAC_OK;
+}
+
 static int decode_image(Engine *e, const uint8_t *sac, size_t len, std::vector<uint8_t> &out, sac_file_stats *st)
 {
   const auto t0 = std::chrono::steady_clock::now();
@@ -1571,6 +1631,61 @@ int sac_encode_file(sac_engine *h, const sac_cfg *cfg, const char *wav_path, con
   if (rc) return rc;
   return write_file(sac_path, out);
 }
+int sac_encode_file_multi(sac_engine *const *engines, int nengines, const sac_cfg *cfg, const char *wav_path, const char *sac_path, sac_file_stats *st)
+{
+  if (!engines || nengines < 1 || !cfg || !wav_path || !sac_path) { set_error("sac_encode_file_multi: bad argument"); return SAC_E_ARG; }
+  for (int i = 0; i < nengines; i++) if (!engines[i]) { set_error("sac_encode_file_multi: null engine"); return SAC_E_ARG; }
+  std::vector<uint8_t> in, out;
+  int rc = read_file(wav_path, in);
+  if (rc) return rc;
+  rc = encode_image_multi(reinterpret_cast<Engine *const *>(engines), nengines, *cfg, in.data(), in.size(), out, st);
+  if (rc) return rc;
+  return write_file(sac_path, out);
+}
+
+// Codec::EncodeFile over a batch (config C4): files are independent, so every engine (GPU) takes the next file off a queue
+// ordered longest first and encodes it with its frames in flight; nothing is exchanged between the GPUs.
+int sac_encode_files(sac_engine *const *engines, int nengines, const sac_cfg *cfg, int nfiles, const char *const *wav_paths,
+                     const char *const *sac_paths, sac_file_stats *stats, int *status)
+{
+  if (!engines || nengines < 1 || !cfg || nfiles < 0 || (nfiles && (!wav_paths || !sac_paths))) { set_error("sac_encode_files: bad argument"); return SAC_E_ARG; }
+  for (int i = 0; i < nengines; i++) if (!engines[i]) { set_error("sac_encode_files: null engine"); return SAC_E_ARG; }
+  for (int i = 0; i < nfiles; i++)
+    for (int j = 0; j < i; j++)
+      if (std::string(sac_paths[i]) == sac_paths[j]) { set_error(std::string("sac_encode_files: two inputs map to the same output ") + sac_paths[i]); return SAC_E_ARG; }
+  std::vector<std::pair<long long, int>> order;                      // (size, index), longest first
+  for (int i = 0; i < nfiles; i++) {
+    std::ifstream f(wav_paths[i], std::ios::binary | std::ios::ate);
+    order.push_back({f ? (long long)f.tellg() : -1, i});
+  }
+  std::sort(order.begin(), order.end(), [](const std::pair<long long, int> &a, const std::pair<long long, int> &b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+  std::vector<int> rcs(nfiles, SAC_OK);
+  std::vector<std::string> errs(nfiles);
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  sac_cfg c = *cfg;
+  if (c.frame_parallel == 0) { c.frame_parallel = 2; c.reset = 1; }   // frames of a file in flight together
+  for (int g = 0; g < std::min(nengines, std::max(nfiles, 1)); g++)
+    th.emplace_back([&, g]() {
+      Engine *e = reinterpret_cast<Engine *>(engines[g]);
+      cudaSetDevice(e->device);
+      for (;;) {
+        const int k = next.fetch_add(1);
+        if (k >= nfiles) break;
+        const int i = order[k].second;
+        rcs[i] = sac_encode_file(engines[g], &c, wav_paths[i], sac_paths[i], stats ? stats + i : nullptr);
+        if (rcs[i]) errs[i] = sac_last_error();
+      }
+    });
+  for (auto &t : th) t.join();
+  int first_bad = SAC_OK;
+  for (int i = 0; i < nfiles; i++) {
+    if (status) status[i] = rcs[i];
+    if (rcs[i] && first_bad == SAC_OK) { first_bad = rcs[i]; set_error(std::string(wav_paths[i]) + ": " + errs[i]); }
+  }
+  return first_bad;
+}
+
 int sac_decode_file(sac_engine *h, const char *sac_path, const char *wav_path, sac_file_stats *st)
 {
   Engine *e = reinterpret_cast<Engine *>(h);

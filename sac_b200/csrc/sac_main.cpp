@@ -113,7 +113,7 @@ int main(int argc, const char *argv[])
   sac_cfg_default(&cfg);
   std::string in, out;
   bool first = true;
-  int gpu = 0;
+  int gpu = 0, gpus = 1;
   int mt_mode = 2;                                                    // tsac_cfg default (libsac.h:19-44); listings echo it
   bool gen_given = false;                                             // --opt-cfg=...,N seen
   for (int k = 1; k < argc; k++) {
@@ -167,6 +167,7 @@ int main(int argc, const char *argv[])
       } else if (key == "--ADAPT-BLOCK") cfg.adapt_block = !(val == "NO" || val == "0");
       else if (key == "--ZERO-MEAN") cfg.zero_mean = !(val == "NO" || val == "0");
       else if (key == "--GPU") gpu = std::atoi(val.c_str());
+      else if (key == "--GPUS") gpus = (val == "ALL" || val.empty()) ? sac_device_count() : std::clamp(std::atoi(val.c_str()), 1, 64);   // frames of the file across the box's GPUs (implies --opt-reset)
       else if (key == "--FRAME-PARALLEL") cfg.frame_parallel = val.empty() ? 2 : std::max(0, std::min(2, std::atoi(val.c_str())));
       else if (key == "--SPEC") cfg.spec = std::clamp(std::atoi(val.c_str()), 1, 256);          // candidates per speculative batch
       else if (key == "--INFLIGHT") cfg.inflight = std::clamp(std::atoi(val.c_str()), 1, 64);   // frames in flight (--frame-parallel=2)
@@ -229,7 +230,19 @@ int main(int argc, const char *argv[])
       std::printf("  B200: %s %d, frame-parallel %d (in flight %d), search grade %d, gpu %d\n", cfg.num_threads > 0 || cfg.search != SAC_SEARCH_DDS ? "generation" : "speculative batch",
                   cfg.search == SAC_SEARCH_DE ? 30 : (cfg.search == SAC_SEARCH_CMA ? 1 : (cfg.num_threads > 0 ? cfg.num_threads : cfg.spec)), cfg.frame_parallel, cfg.inflight, cfg.grade, gpu);
     std::printf("\n");
-    rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
+    if (gpus > 1) {
+      std::vector<sac_engine *> engs{eng};
+      const int ndev = sac_device_count();
+      for (int d = 0; d < ndev && (int)engs.size() < gpus; d++) {
+        if (d == gpu) continue;
+        sac_engine *x = sac_engine_create(d);
+        if (!x) { std::cerr << "error: " << sac_last_error() << "\n"; return 1; }
+        engs.push_back(x);
+      }
+      std::printf("  B200: %d GPUs, frames dealt round-robin (--opt-reset semantics)\n\n", (int)engs.size());
+      rc = sac_encode_file_multi(engs.data(), (int)engs.size(), &cfg, in.c_str(), out.c_str(), &st);
+      for (size_t i = 1; i < engs.size(); i++) sac_engine_destroy(engs[i]);
+    } else rc = sac_encode_file(eng, &cfg, in.c_str(), out.c_str(), &st);
     if (rc) { std::cerr << "error: " << sac_last_error() << "\n"; sac_engine_destroy(eng); return 1; }
     std::printf("  %d/%d: 100.0%%\n", st.numsamples, st.numsamples);
     std::printf("  MD5:     "); print_md5(st.md5); std::printf("\n");

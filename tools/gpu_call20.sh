@@ -2,7 +2,9 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-/usr/bin/time -v timeout -s KILL 860 python bench.py --steps 20 --warmup 5 --gen 128 --inflight 20 > gpurun_out/c20_bench.json 2> gpurun_out/c20_bench.err
+T0=$SECONDS
+timeout -s KILL 860 python bench.py --steps 20 --warmup 5 --gen 128 --inflight 20 > gpurun_out/c20_bench.json 2> gpurun_out/c20_bench.err
+echo "bench wall $((SECONDS-T0)) s rc=$?"
 python - <<'PY'
 import json
 try:
@@ -10,4 +12,4 @@ try:
     print({k:d[k] for k in ('value','ms_per_step','bps','gpu_launches')}, d['chains'], d['device_ms_by_kernel_class'], d['kernel_ms_per_generation'], d['cpu_baseline']['value'])
 except Exception as e: print("no json", e)
 PY
-grep -E "Elapsed|Maximum resident" gpurun_out/c20_bench.err; tail -3 gpurun_out/c20_bench.err | cut -c1-300
+tail -3 gpurun_out/c20_bench.err | cut -c1-300
