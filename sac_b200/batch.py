@@ -25,25 +25,41 @@ def assign_files(sizes, world):
     return [sorted(x) for x in out]
 
 
+def output_names(paths):
+    """basename + '.sac' per input; two inputs with the same basename (a/x.wav, b/x.wav) would overwrite each other: refused"""
+    names = [os.path.splitext(os.path.basename(p))[0] + ".sac" for p in paths]
+    seen = {}
+    for p, n in zip(paths, names):
+        if n in seen:
+            raise ValueError("inputs %s and %s would both be written to %s" % (seen[n], p, n))
+        seen[n] = p
+    return names
+
+
 def encode_batch(paths, out_dir, encode_fn, rank=0, world=1, device=None):
     """encode_fn(wav_bytes) -> sac_bytes (this rank's GPU), or a list of such callables = that many files in flight on
     this GPU (one engine each). Every rank must call this with the same `paths`.
     Returns on rank 0: [(path, in_bytes, out_bytes)] in input order, and the seconds of the slowest rank (device-timed by
     the caller's encode_fn; here: wall around this rank's files, max over ranks)."""
     from . import shard
+    dst_names = output_names(paths)                                 # refuses two inputs that would overwrite each other
     sizes = [os.path.getsize(p) for p in paths]
     mine = assign_files(sizes, world)[rank]
     fns = list(encode_fn) if isinstance(encode_fn, (list, tuple)) else [encode_fn]
     t0 = time.perf_counter()
     local = {}
+    failure = None
 
     def one(i, fn):
         with open(paths[i], "rb") as f:
             return i, fn(f.read())
 
     if len(fns) == 1:
-        for i in mine:
-            local[i] = one(i, fns[0])[1]
+        try:
+            for i in mine:
+                local[i] = one(i, fns[0])[1]
+        except Exception as e:                  # keep going to the collectives below: the other ranks are waiting there
+            failure = e
     else:
         # several files in flight on this GPU (one engine each): a file of one or two frames does not fill the machine.
         # Longest files first; a worker takes the next file as soon as it is free.
@@ -70,7 +86,13 @@ def encode_batch(paths, out_dir, encode_fn, rank=0, world=1, device=None):
         for t in th: t.start()
         for t in th: t.join()
         if errs:
-            raise errs[0]
+            failure = errs[0]
+    # a rank that failed must still meet the others in the collectives, or they hang: agree on the failure first
+    nfail = shard.sum_over_ranks(1 if failure is not None else 0, device)
+    if nfail:
+        if failure is not None:
+            raise failure
+        raise RuntimeError("encode_batch: %d other rank(s) failed" % nfail)
     secs = shard.max_over_ranks(time.perf_counter() - t0, device)
     got = _gather(local, len(paths), mine, rank, world, device)
     if rank != 0:
@@ -78,7 +100,7 @@ def encode_batch(paths, out_dir, encode_fn, rank=0, world=1, device=None):
     os.makedirs(out_dir, exist_ok=True)
     rep = []
     for i, p in enumerate(paths):
-        dst = os.path.join(out_dir, os.path.splitext(os.path.basename(p))[0] + ".sac")
+        dst = os.path.join(out_dir, dst_names[i])
         with open(dst, "wb") as f:
             f.write(got[i])
         rep.append((p, sizes[i], len(got[i])))
@@ -142,7 +164,7 @@ def main(argv=None):
     cfg = sb.make_cfg(preset)
     if cfg.optimize:
         cfg.num_threads = gen if gen else min(128, max(1, (cfg.maxnfunc + 7) // 8))    # about 8 generations, as the CLI
-    cfg.frame_parallel = 2; cfg.reset = 1               # frames of a file in flight together (--opt-reset semantics)
+    cfg.frame_parallel = 2; cfg.reset = 1; cfg.grade = 1; cfg.inflight = 8   # frames of a file in flight together (--opt-reset semantics), search-grade kernels for the search
     fns = [(lambda wav, e=e: e.encode_memory(cfg, wav)[0]) for e in engines]
     rep, secs = encode_batch(files, out_dir, fns, rank, world, dev)
     if rank == 0:

@@ -57,6 +57,15 @@ def max_over_ranks(value, device=None):
     return float(t.item())
 
 
+def sum_over_ranks(value, device=None):
+    """integer sum over the ranks (e.g. how many of them failed, agreed BEFORE the next collective so that nobody hangs)"""
+    if not (dist.is_available() and dist.is_initialized()):
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device if device is not None else torch.device("cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
 def sharded_population_costs(eval_rows, X, rank, world, device=None):
     """X[P, D]: the generation, identical on every rank. eval_rows(X_sub) -> costs of those rows (this rank's GPU).
     Returns the full cost vector [P] on every rank, bit-identical everywhere (float64 through the collective).

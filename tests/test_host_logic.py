@@ -397,3 +397,19 @@ def test_speculative_search_with_ties_nan_and_constant_costs():
                     continue                                         # cost depends on the position in the batch: not a function of x
                 b1, x1, ev = sb.dds_run_spec(fn, xmin, xmax, xs, nf, 0.2, spec)
                 assert (b1 == b0 or (np.isnan(b1) and np.isnan(b0))) and np.array_equal(x1, x0), (nf, spec)
+
+
+def test_batch_entry_point_validates_its_arguments_without_a_gpu(tmp_path):
+    """sac_encode_files / sac_encode_file_multi (several GPUs from the C++ host): argument errors are reported before any device
+    work -- null engines, and two inputs that would be written to the same output path"""
+    import ctypes as C
+    L = sb.lib()
+    cfg = sb.make_cfg("normal")
+    st = sb.FileStats()
+    none = (C.c_void_p * 1)(None)
+    assert L.sac_encode_file_multi(none, 1, C.byref(cfg), b"a.wav", b"a.sac", C.byref(st)) == -3      # SAC_E_ARG
+    assert L.sac_encode_files(none, 1, C.byref(cfg), 0, None, None, None, None) == -3
+    fake = (C.c_void_p * 1)(C.c_void_p(1))                        # never dereferenced: the duplicate check comes first
+    wp = (C.c_char_p * 2)(b"x/a.wav", b"y/a.wav"); sp = (C.c_char_p * 2)(b"out/a.sac", b"out/a.sac")
+    assert L.sac_encode_files(fake, 1, C.byref(cfg), 2, wp, sp, None, None) == -3
+    assert b"same output" in L.sac_last_error()

@@ -149,3 +149,46 @@ def test_two_rank_file_batch(tmp_path):
         img = open(os.path.join(out_dir, "f%d.sac" % i), "rb").read()
         assert img[:4] == b"SAC2" and zlib.decompress(img[4:]) == open(p, "rb").read()
     assert res[0][3] == res[1][3] > 0
+
+
+def _failing_batch_worker(rank, world, port, q, paths, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from sac_b200 import batch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def encode(wav):
+        if rank == 1:
+            raise RuntimeError("encoder failed on rank 1")
+        return b"SAC2" + wav[:4]
+
+    try:
+        batch.encode_batch(paths, out_dir, encode, rank, world)
+        q.put((rank, "returned"))
+    except Exception as e:                      # BOTH ranks must get here: the healthy one is told, nobody hangs in a collective
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_file_batch_failure_reaches_every_rank_and_duplicate_outputs_are_refused(tmp_path):
+    import pytest
+    sys.path.insert(0, ROOT)
+    from sac_b200 import batch
+    paths = []
+    for i in range(4):
+        p = str(tmp_path / ("g%d.wav" % i)); open(p, "wb").write(bytes(100 + i)); paths.append(p)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_failing_batch_worker, args=(r, 2, port, q, paths, str(tmp_path / "o"))) for r in range(2)]
+    for p in procs: p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs: p.join(60)
+    assert "failed on rank 1" in res[1] and "other rank(s) failed" in res[0]
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    for d in ("a", "b"):
+        open(tmp_path / d / "x.wav", "wb").write(b"1234")
+    with pytest.raises(ValueError, match="would both be written"):
+        batch.output_names([str(tmp_path / "a" / "x.wav"), str(tmp_path / "b" / "x.wav")])
