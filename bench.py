@@ -340,7 +340,7 @@ def main():
             # residual in + S2U-mapped back in place (8 B), then one 4-B read per coded plane, cost out
             "bitplane": (bp_s, chains * W * (8 + 4 * planes_coded) + chains * 8),
         }
-        names = {"ols": "ols_sg_kernel" if args.grade else "ols_kernel", "cascade": "cascade_sg_kernel" if args.grade else "cascade_kernel",
+        names = {"ols": "ols_warp_kernel" if args.grade else "ols_kernel", "cascade": "cascade_sg_kernel" if args.grade else "cascade_kernel",
                  "bitplane": "bitplane_pipe_kernel"}
         share = {"ols": tm_timed[0], "cascade": tm_timed[1], "bitplane": tm_timed[2]}
         tot = sum(share.values()) or 1.0
