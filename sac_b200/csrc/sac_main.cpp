@@ -183,11 +183,13 @@ int main(int argc, const char *argv[])
     std::printf("\n  Time:    [00:00:00]\n");                          // cmdline.cpp:355-356
     return rc;
   }
-  // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step. It stays the
-  // default here and is evaluated in speculative batches (sac_cfg::spec, sac_dds_run_spec): same accepted sequence and
-  // result as one candidate at a time, but tens of chains per launch. --opt-cfg=dds,N (N > 0) selects the reference's
-  // population variant (OptDDS::run_mt, dds.cpp:63-106) as it does there.
-  (void)gen_given;
+  // The reference's default search is sequential (toptim_cfg::num_threads = 0, libsac.h:26): one candidate per step. On a GPU that
+  // is a chain of ~100 dependent launches per frame even in speculative batches (sac_cfg::spec), each as long as its slowest
+  // candidate: minutes for seconds of audio. Unless the user says otherwise the CLI therefore runs the reference's own population
+  // variant (OptDDS::run_mt, dds.cpp:63-106) in about 8 generations (an eighth of the evaluation budget per generation, at most
+  // 128: --best -> 125, --high -> 13). --opt-cfg=dds,0 selects the reference's sequential search, executed in speculative batches
+  // (same accepted sequence and result as one candidate at a time).
+  if (mode == ENCODE && cfg.optimize && cfg.search == SAC_SEARCH_DDS && !gen_given) cfg.num_threads = std::clamp((cfg.maxnfunc + 7) / 8, 1, 128);
   // console output mirrors CmdLine::Process (cmdline.cpp:245-358): Open / PrintWav / Create / PrintMode / MD5 / ratio line
   const auto t_all = std::chrono::steady_clock::now();
   std::vector<uint8_t> img;
