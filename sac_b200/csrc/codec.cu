@@ -143,8 +143,10 @@ void DdsSearch::consume(const double *costs)
   {                                                                     // run_mt + SSC1 (dds.cpp:88-98, ssc.h:40-60)
     const double fb_old = fb_;
     int nsucc = 0;
-    for (int i = 0; i < nt; i++)
+    for (int i = 0; i < nt; i++) {
+      if (trace_on_) trace_.emplace_back(costs[i], pending_[i]);
       if (costs[i] < fb_old) { nsucc++; if (costs[i] < fb_) { fb_ = costs[i]; xb_ = pending_[i]; } }
+    }
     const double lambda = nsucc / static_cast<double>(nt);
     p_succ_ = (1.0 - 0.10) * p_succ_ + 0.10 * lambda;
     sigma_ = sigma_ * std::exp(0.05 * (p_succ_ - 0.05) / (1.0 - 0.05));
