@@ -632,7 +632,10 @@ static int frames_encode_seq(Engine *e, const sac_cfg &cfg, int nch, int max_fra
                              const int *numsamples, float *profile_io, std::vector<uint8_t> &out,
                              const sac_window *const *resident, const int32_t *resident_means)
 {
-  e->grade = cfg.grade ? 1 : 0;                                      // arithmetic of the search evaluations; final passes are canonical
+  // arithmetic of the search evaluations for the duration of this call (final passes are canonical); the engine's own setting
+  // (sac_engine_set_grade, used by sac_predict / sac_eval_*) is restored on every way out
+  struct GradeGuard { Engine *e; int prev; ~GradeGuard() { e->grade = prev; } } grade_guard{e, e->grade};
+  e->grade = cfg.grade ? 1 : 0;
   std::vector<FrameWork> fw(nframes);
   struct Cleanup { std::vector<FrameWork> &f; bool own; ~Cleanup() { if (own) for (auto &x : f) if (x.win) sac_window_destroy(reinterpret_cast<sac_window *>(x.win)); } } cleanup{fw, resident == nullptr};
   // ---- analysis + upload (or windows already resident in HBM) ----
