@@ -224,7 +224,7 @@ def test_recorded_bench_lines_follow_the_contract():
     cpu_baseline, e2e with the copied bytes, clocks, launch count)"""
     import json
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    for fn in ("bench_r1_n1.json", "bench_r1_n2_nfunc129.json"):
+    for fn in ("bench_r1_n1.json", "bench_r1_n2_nfunc129.json", "bench_r2_n1.json"):
         d = json.load(open(os.path.join(ROOT, "profiles", fn)))
         assert d["metric"].split(";")[0] in base["metric"] and d["unit"] == "MSamples/s" and d["higher_is_better"] is True
         for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches"):

@@ -3,6 +3,7 @@ evaluated candidate of ONE frame's search, in order -- the candidates bench.py's
 usage: SACB_TRACE_DDS=gpurun_out/trace.jsonl python bench.py ... ; python tools/make_bench_candidates.py gpurun_out/trace.jsonl"""
 import json, sys
 rows = [json.loads(l) for l in open(sys.argv[1])]
+rows = [r for r in rows if r["frame_n"] == 882000]   # the timed frames (the warm-up runs 2-s excerpts)
 first = []
 for r in rows:                                   # the first frame written (steps restart at 1 for the next one)
     if first and r["step"] <= first[-1]["step"]:
