@@ -166,7 +166,7 @@ cudaError_t launch_ols_canonical(const ChainDesc *d_descs, const int *d_idx, int
 // search-grade kernels (predictor_sg.cu)
 cudaError_t predictor_sg_init_attributes();
 size_t cascade_sg_smem_bytes(const int *vn, int large);          // 0: the chain does not fit that variant
-int ols_sg_class(int n_ols);                                     // 3, 5 or 7 (16-wide blocks per matrix dimension)
+int ols_sg_class(int n_ols);                                     // 16 / 24 / 32 (one warp per chain), 64 (experiment), 0 = canonical kernel
 size_t ols_sg_smem_bytes(int n_ols);
 cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream);
 cudaError_t launch_cascade_sg(const ChainDesc *d_descs, const int *d_idx, int count, int large, int smem_bytes, cudaStream_t stream);

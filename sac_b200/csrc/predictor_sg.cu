@@ -17,11 +17,12 @@
 //        8 tap warps (taps j >= 1 in per-thread contiguous blocks of odd length, weights in registers, tables and history in
 //        shared memory) + S (stage predictions, mix, targets, gradients; owns tap 0) + M (mix update) + R (RLS stage, its
 //        matrix-vector part computed ahead of the sample) + B (bias stage, residual, trails by one sample).
-//  ols_sg_kernel<NB>  256 threads per chain. Covariance and work matrix live in REGISTERS, lower triangle, 16 x 16 block-cyclic
-//        over the thread grid (element (i,c) on thread (i mod 16, c mod 16)); the k rank-1 updates of a block are one fused
-//        rank-k update (on the DMMA-shaped Gram product see DESIGN.md); right-looking LDL^T exchanges one column per step
-//        through a double-buffered shared-memory vector (one barrier per column, ~25 instructions per thread and column
-//        instead of ~300); L goes to shared memory packed by rows for the back substitution on warp 0.
+//  ols_warp_kernel<NP>  orders n <= NP <= 32: ONE WARP per chain, four chains per CTA, lane i owns row i of the covariance and
+//        of the work matrix in REGISTERS; right-looking LDL^T exchanges one column per step through a double-buffered
+//        shared-memory vector (one __syncwarp per column); L goes to shared memory by rows for the back substitution.
+//        Orders above 32 stay on the canonical team kernel (predictor_enc.cu): a 256-thread block-cyclic register kernel and a
+//        two-warp rows-in-registers kernel were both measured slower than it on the B200 (profiles/README.md, round 2); the
+//        latter is kept behind SACB_OLS_ROWS=1 (ols_rows_kernel) as the record of that experiment.
 //
 // Results equal the canonical kernels' up to rounding: residuals differ in isolated samples where a prediction lies within
 // ~1e-12 of a rounding boundary. tests/test_gpu_grade.py states and checks the tolerance (costs, ranking).
@@ -64,11 +65,6 @@ __device__ __forceinline__ double rcp_fast(double x)
   e = fma(-x, y, 1.0);
   y = fma(y, e, y);
   return y;
-}
-__device__ __forceinline__ double butterfly(double v)
-{
-  v += shfl_xor(v, 16); v += shfl_xor(v, 8); v += shfl_xor(v, 4); v += shfl_xor(v, 2); v += shfl_xor(v, 1);
-  return v;
 }
 
 // =====================================================================================================================
@@ -657,216 +653,8 @@ __global__ void __launch_bounds__(CFG::threads, (CFG::tw == 4 ? 2 : 1)) cascade_
 // =====================================================================================================================
 // OLS
 // =====================================================================================================================
-constexpr int kOT = 256;                                             // threads: 16 x 16 grid
 constexpr int kOXW = 256;                                            // input window (samples, power of two)
-constexpr int kOXS = 116;                                            // row stride of the regressor block (>= 16 * 7 + 1)
 constexpr int kOKB = 4;                                              // samples per block
-
-struct OlsSgShared {
-  double X[kOKB][kOXS];
-  double xo[kOXW], xq[kOXW];
-  double col[2][kOXS];
-  double pu[kOKB], ff[kOKB];
-  double wv[kMaxOls], z[kMaxOls];
-};
-
-template <int NB>
-__global__ void __launch_bounds__(kOT, (NB <= 3 ? 3 : (NB <= 5 ? 2 : 1))) ols_sg_kernel(const ChainDesc *__restrict__ descs, const int *__restrict__ idx)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ChainDesc &d = descs[idx ? idx[blockIdx.x] : blockIdx.x];
-  OlsSgShared &S = *reinterpret_cast<OlsSgShared *>(smem_raw);
-  double *Ls = reinterpret_cast<double *>(smem_raw + ((sizeof(OlsSgShared) + 15) & ~size_t(15)));   // L packed by rows: row k at k(k-1)/2
-  const int tid = threadIdx.x, lane = tid & 31, tw = tid >> 5;
-  const int r = tid >> 4, q = tid & 15;
-  const int N = d.n;
-  const int n = d.lenA + d.lenB, n1 = n + 1;
-  const double lambda = d.lambda, nu = d.nu, one_m_lambda = 1.0 - d.lambda;
-  constexpr int NP = NB * (NB + 1) / 2;
-  double cv[NP], wk[NP];
-  bool valid[NP];
-  {
-    int p = 0;
-#pragma unroll
-    for (int a = 0; a < NB; a++)
-#pragma unroll
-      for (int b = 0; b <= a; b++, p++) {
-        const int i = r + 16 * a, c = q + 16 * b;
-        valid[p] = i <= n && c <= i && c < n;
-        cv[p] = 0.0; wk[p] = 0.0;
-      }
-  }
-  for (int i = tid; i < kMaxOls; i += kOT) S.wv[i] = 0.0;
-  double w0 = 0.0, w1 = 0.0, w2 = 0.0;                               // w[lane], w[lane+32], w[lane+64] (every warp its copy)
-  double esum = 0.0;
-  int km = 0;
-  for (int qq = tid; qq < 192; qq += kOT) {
-    const int ix = qq - 64;
-    const bool in = ix >= 0 && ix < N;
-    S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
-    S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
-  }
-  int fill_end = 128;
-  int t = 0;
-  while (t < N) {
-    if (fill_end < t + 68) {
-      if (tid < 64) {
-        const int ix = fill_end + tid;
-        const bool in = ix < N;
-        S.xo[ix & (kOXW - 1)] = in ? (double)__ldg(d.own + ix) : 0.0;
-        S.xq[ix & (kOXW - 1)] = in ? (double)__ldg(d.other + ix) : 0.0;
-      }
-      fill_end += 64;
-    }
-    const int kb = min(min(kOKB, d.k - km), N - t);
-    __syncthreads();
-    // ---- regressors of the block: X[u][0..n), X[u][n] = sample (pred.cpp:17-31) ----
-    for (int e = tid; e < kb * n1; e += kOT) {
-      const int u = e / n1, j = e - u * n1;
-      const int tt = t + u;
-      const int sB = max(tt - d.lagB, d.minB) - d.backB;
-      double v;
-      if (j < d.lenA) v = S.xo[(tt - d.lenA + j) & (kOXW - 1)];
-      else if (j < n) v = S.xq[(sB + j - d.lenA) & (kOXW - 1)];
-      else v = S.xo[tt & (kOXW - 1)];
-      S.X[u][j] = v;
-    }
-    __syncthreads();
-    // ---- predictions: warp u takes sample u (ols.cpp:22-25) ----
-    if (tw < kb) {
-      double acc = 0.0;
-      if (lane < n) acc = fma(S.X[tw][lane], w0, acc);
-      if (lane + 32 < n) acc = fma(S.X[tw][lane + 32], w1, acc);
-      if (lane + 64 < n) acc = fma(S.X[tw][lane + 64], w2, acc);
-      acc = butterfly(acc);
-      if (lane == 0) { S.pu[tw] = acc; d.plpc[t + tw] = acc; }
-    }
-    __syncthreads();
-    // ---- IRLS weights (ols.cpp:29-36): serial running sum (every thread), one power per thread u < kb ----
-    {
-      double es_mine = 1.0;
-#pragma unroll
-      for (int u = 0; u < kOKB; u++)
-        if (u < kb) {
-          esum = fma(d.beta_sum, esum, fabs(S.X[u][n] - S.pu[u]));
-          if (tid == u) es_mine = esum;
-        }
-      if (tid < kb) S.ff[tid] = one_m_lambda * c_pow(es_mine + d.beta_add, -d.beta_pow);
-    }
-    __syncthreads();
-    // ---- covariance: the kb rank-1 updates of the block as one rank-kb update (ols.cpp:38-45) ----
-    km += kb;
-    const bool solve = km >= d.k;
-    {
-      double fu[kOKB], lamk = 1.0;
-#pragma unroll
-      for (int u = kOKB - 1; u >= 0; u--) { fu[u] = u < kb ? S.ff[u] * lamk : 0.0; if (u < kb) lamk *= lambda; }
-#pragma unroll
-      for (int p = 0; p < NP; p++) cv[p] *= lamk;
-#pragma unroll
-      for (int u = 0; u < kOKB; u++) {
-        if (u < kb) {                                                // uniform
-          double fx[NB], xc[NB];
-#pragma unroll
-          for (int a = 0; a < NB; a++) { fx[a] = fu[u] * S.X[u][min(r + 16 * a, n)]; xc[a] = S.X[u][min(q + 16 * a, n)]; }
-          int p = 0;
-#pragma unroll
-          for (int a = 0; a < NB; a++)
-#pragma unroll
-            for (int b = 0; b <= a; b++, p++) cv[p] = fma(fx[a], xc[b], cv[p]);
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < NP; p++) cv[p] = valid[p] ? cv[p] : 0.0;
-    }
-    if (solve) {
-      km = 0;
-      {
-        int p = 0;
-#pragma unroll
-        for (int a = 0; a < NB; a++)
-#pragma unroll
-          for (int b = 0; b <= a; b++, p++) wk[p] = cv[p] + ((a == b && r == q && r + 16 * a < n) ? nu : 0.0);
-      }
-      // ---- right-looking LDL^T of (C + nu I) augmented with b as row n; one column per step through S.col ----
-      if (q == 0) {                                                  // column 0 (b == 0 blocks are pairs (a,0))
-        int p = 0;
-#pragma unroll
-        for (int a = 0; a < NB; a++) { if (r + 16 * a <= n) S.col[0][r + 16 * a] = wk[p]; p += a + 1; }
-      }
-      __syncthreads();
-      bool ok = true;
-      for (int j = 0; j < n; j++) {
-        const double *cb = S.col[j & 1];
-        double *cn = S.col[(j + 1) & 1];
-        const double dj = cb[j];
-        if (dj < 1e-12) { ok = false; break; }
-        const double inv = rcp_fast(dj);
-        double li[NB], uc[NB];
-#pragma unroll
-        for (int a = 0; a < NB; a++) {
-          const int i = r + 16 * a, c = q + 16 * a;
-          li[a] = (i > j && i <= n) ? cb[i] * inv : 0.0;
-          uc[a] = (c > j && c < n) ? cb[c] : 0.0;
-        }
-        const int qn = (j + 1) & 15, bn = (j + 1) >> 4;
-        int p = 0;
-#pragma unroll
-        for (int a = 0; a < NB; a++)
-#pragma unroll
-          for (int b = 0; b <= a; b++, p++) {
-            const int c = q + 16 * b;
-            if (valid[p] && c > j) {
-              const double v = fma(-li[a], uc[b], wk[p]);
-              wk[p] = v;
-              if (q == qn && b == bn) cn[r + 16 * a] = v;             // next column: rows >= j+1 (c = j+1)
-            }
-          }
-        if (q == 0) {                                                // L[i][j] = W[i][j] / d_j by rows; row n of L is z = D^-1 L^-1 b
-#pragma unroll
-          for (int a = 0; a < NB; a++) {
-            const int i = r + 16 * a;
-            if (i > j && i < n) Ls[(i * (i - 1)) / 2 + j] = li[a];
-            else if (i == n) S.z[j] = li[a];
-          }
-        }
-        __syncthreads();
-      }
-      if (ok && tw == 0) {
-        // back substitution L^T w = z, columns in descending order; row k of L is contiguous
-        double y0 = lane < n ? S.z[lane] : 0.0;
-        double y1 = lane + 32 < n ? S.z[lane + 32] : 0.0;
-        double y2 = lane + 64 < n ? S.z[lane + 64] : 0.0;
-        double l0 = 0.0, l1 = 0.0, l2 = 0.0;
-        if (n >= 2) {
-          const double *row = Ls + ((n - 1) * (n - 2)) / 2;
-          l0 = lane < n - 1 ? row[lane] : 0.0; l1 = lane + 32 < n - 1 ? row[lane + 32] : 0.0; l2 = lane + 64 < n - 1 ? row[lane + 64] : 0.0;
-        }
-        for (int k = n - 1; k >= 1; k--) {
-          const double c0 = l0, c1 = l1, c2 = l2;
-          if (k >= 2) {                                              // next row, fetched one step ahead
-            const double *row = Ls + ((k - 1) * (k - 2)) / 2;
-            l0 = lane < k - 1 ? row[lane] : 0.0; l1 = lane + 32 < k - 1 ? row[lane + 32] : 0.0; l2 = lane + 64 < k - 1 ? row[lane + 64] : 0.0;
-          }
-          const int sl = k >> 5;
-          double yk = sl == 0 ? y0 : (sl == 1 ? y1 : y2);
-          yk = shfl_idx(yk, k & 31);
-          y0 = fma(-c0, yk, y0); y1 = fma(-c1, yk, y1); y2 = fma(-c2, yk, y2);   // rows beyond k-1 carry zeros
-        }
-        if (lane < n) S.wv[lane] = y0;
-        if (lane + 32 < n) S.wv[lane + 32] = y1;
-        if (lane + 64 < n) S.wv[lane + 64] = y2;
-      }
-      __syncthreads();
-      if (ok) {
-        w0 = lane < n ? S.wv[lane] : 0.0;
-        w1 = lane + 32 < n ? S.wv[lane + 32] : 0.0;
-        w2 = lane + 64 < n ? S.wv[lane + 64] : 0.0;
-      }
-    }
-    t += kb;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ols_warp_kernel<NP>: orders n <= NP <= 32, ONE WARP per chain, four independent chains per CTA, no CTA barrier in the loop.
@@ -1248,24 +1036,21 @@ size_t cascade_sg_smem_bytes(const int *vn, int large)
   }
   return ((sizeof(SgShared) + 15) & ~size_t(15)) + doubles * 8 + 64;
 }
-// OLS kernel classes: orders up to 32 run one warp per chain (ols_warp_kernel<16 / 24 / 32>, classes 16 / 24 / 32), larger ones
-// the 256-thread block-cyclic kernel with 3, 5 or 7 blocks of 16 per matrix dimension (classes 3 / 5 / 7)
+// OLS kernel classes: orders up to 32 run one warp per chain (ols_warp_kernel<16 / 24 / 32>, classes 16 / 24 / 32); 64 = the
+// two-warp experiment (ols_rows_kernel<2>); 0 = no search-grade kernel for this order (canonical team kernel)
 int ols_sg_class(int n_ols)
 {
   if (n_ols <= 16) return 16;
   if (n_ols <= 24) return 24;
   if (n_ols <= 32) return 32;
   if (n_ols <= 64) return 64;
-  if (n_ols <= 96) return 96;
-  const int nb = (n_ols + 1 + 15) / 16;
-  return nb <= 3 ? 3 : (nb <= 5 ? 5 : 7);
+  return 0;
 }
 size_t ols_sg_smem_bytes(int n_ols)
 {
   if (n_ols <= 32) return 4 * sizeof(OlsWarpShared) + 64;
   if (n_ols <= 64) return ((sizeof(OlsRowsShared<2>) + 15) & ~size_t(15)) + (tri_index(64) + tri_index(63)) * 8 + 64;
-  if (n_ols <= 96) return ((sizeof(OlsRowsShared<3>) + 15) & ~size_t(15)) + (tri_index(96) + tri_index(95)) * 8 + 64;
-  return ((sizeof(OlsSgShared) + 15) & ~size_t(15)) + (size_t)(n_ols * (n_ols - 1) / 2 + 8) * 8;
+  return 0;
 }
 
 cudaError_t predictor_sg_init_attributes()
@@ -1275,30 +1060,20 @@ cudaError_t predictor_sg_init_attributes()
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(cascade_sg_kernel<SgLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(ols_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(ols_warp_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(ols_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(ols_sg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(ols_sg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(ols_sg_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  return cudaFuncSetAttribute(ols_warp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
 }
 
 cudaError_t launch_ols_sg(const ChainDesc *d_descs, const int *d_idx, int count, int nb_class, int smem_bytes, cudaStream_t stream)
 {
   if (count <= 0) return cudaSuccess;
   if (nb_class == 64) { ols_rows_kernel<2><<<count, 64, smem_bytes, stream>>>(d_descs, d_idx); return cudaGetLastError(); }
-  if (nb_class == 96) { ols_rows_kernel<3><<<count, 96, smem_bytes, stream>>>(d_descs, d_idx); return cudaGetLastError(); }
-  if (nb_class >= 16) {
-    const int grid = (count + 3) / 4;
-    if (nb_class == 16) ols_warp_kernel<16><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
-    else if (nb_class == 24) ols_warp_kernel<24><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
-    else ols_warp_kernel<32><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
-    return cudaGetLastError();
-  }
-  if (nb_class == 3) ols_sg_kernel<3><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
-  else if (nb_class == 5) ols_sg_kernel<5><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
-  else ols_sg_kernel<7><<<count, kOT, smem_bytes, stream>>>(d_descs, d_idx);
+  const int grid = (count + 3) / 4;
+  if (nb_class == 16) ols_warp_kernel<16><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+  else if (nb_class == 24) ols_warp_kernel<24><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+  else if (nb_class == 32) ols_warp_kernel<32><<<grid, 128, smem_bytes, stream>>>(d_descs, d_idx, count);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 cudaError_t launch_cascade_sg(const ChainDesc *d_descs, const int *d_idx, int count, int large, int smem_bytes, cudaStream_t stream)
