@@ -224,7 +224,7 @@ def test_recorded_bench_lines_follow_the_contract():
     cpu_baseline, e2e with the copied bytes, clocks, launch count)"""
     import json
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    for fn in ("bench_r1_n1.json", "bench_r1_n2_nfunc129.json", "bench_r2_n1.json"):
+    for fn in ("bench_r1_n1.json", "bench_r1_n2_nfunc129.json", "bench_r2_n1.json", "bench_r2_n1_default.json", "bench_r2_n2_nfunc129.json"):
         d = json.load(open(os.path.join(ROOT, "profiles", fn)))
         assert d["metric"].split(";")[0] in base["metric"] and d["unit"] == "MSamples/s" and d["higher_is_better"] is True
         for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "gpu_launches"):
@@ -237,6 +237,30 @@ def test_recorded_bench_lines_follow_the_contract():
         assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         if d["n_gpus"] == 1:
             assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_reference_arm_prints_one_json_line_and_nothing_else():
+    """`bench.py --impl reference` (the CPU arm; the one place outside tests/ that may run oracle/): stdout is ONE JSON line with the
+    contract's keys although the reference's classes print diagnostics with printf; a non-zero rank under torchrun prints nothing"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "MSamples/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["extrapolated"] is True and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "recorded steps of the GPU arm" in d["cpu_baseline"]["sample"]          # timed on the candidates the GPU arm evaluated
+    assert "reference_concurrency" in d["config"] and d["cpu_baseline"]["single_stream_value"] < d["value"]
+    env["RANK"] = "1"; env["WORLD_SIZE"] = "2"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout.strip() == ""
 
 
 def test_dds_first_generation_travels_with_the_start_vector_and_nothing_else_changes():
