@@ -1655,6 +1655,7 @@ int sac_encode_files(sac_engine *const *engines, int nengines, const sac_cfg *cf
 {
   if (!engines || nengines < 1 || !cfg || nfiles < 0 || (nfiles && (!wav_paths || !sac_paths))) { set_error("sac_encode_files: bad argument"); return SAC_E_ARG; }
   for (int i = 0; i < nengines; i++) if (!engines[i]) { set_error("sac_encode_files: null engine"); return SAC_E_ARG; }
+  for (int i = 0; i < nfiles; i++) if (!wav_paths[i] || !sac_paths[i]) { set_error("sac_encode_files: null path"); return SAC_E_ARG; }
   for (int i = 0; i < nfiles; i++)
     for (int j = 0; j < i; j++)
       if (std::string(sac_paths[i]) == sac_paths[j]) { set_error(std::string("sac_encode_files: two inputs map to the same output ") + sac_paths[i]); return SAC_E_ARG; }

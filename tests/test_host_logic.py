@@ -437,3 +437,5 @@ def test_batch_entry_point_validates_its_arguments_without_a_gpu(tmp_path):
     wp = (C.c_char_p * 2)(b"x/a.wav", b"y/a.wav"); sp = (C.c_char_p * 2)(b"out/a.sac", b"out/a.sac")
     assert L.sac_encode_files(fake, 1, C.byref(cfg), 2, wp, sp, None, None) == -3
     assert b"same output" in L.sac_last_error()
+    sp2 = (C.c_char_p * 2)(b"out/a.sac", None)
+    assert L.sac_encode_files(fake, 1, C.byref(cfg), 2, wp, sp2, None, None) == -3 and b"null path" in L.sac_last_error()
