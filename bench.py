@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- encode MSamples/s at --best (stereo 16-bit 44.1 kHz), BASELINE.json's metric.
 
-Workload (config.workload): BASELINE.json configs[2] -- the 60-s stereo synthetic WAV (seed 3 + rank),
+Workload (config.workload): BASELINE.json configs[2] -- the 60-s stereo synthetic WAV (seed 3; every rank its own copy),
 `--best --opt-reset --opt-cfg=dds,128`: per 20-s frame a DDS search of 1000 evaluations (the reference's population variant
 OptDDS::run_mt in generations of 128) of the OLS+NLMS predictor over a 441 000-sample window scored by the real bitplane
 coder, then the final k=1 pass and the payload. The search evaluations run on the search-grade kernels (same formulas,
@@ -22,7 +22,7 @@ chain of ~100 dependent batches per frame -- several times slower on this path (
 Warm-up steps run the same path (every kernel class, engines, streams, pools) on 2-s excerpts with one short generation, so
 that the driver's `--steps 20 --warmup 5` fits its time limit; the timed steps are full frames with the full search.
 `--impl reference` times the reference CPU implementation alone (same metric / config), see reference_arm().
-Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank encodes its own stream (seed 3 + rank); no data-path
+Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank encodes its own copy of the stream (same seed: equal work per GPU, nothing shared or cached across ranks); no data-path
 collective; rank 0 gathers the bitstreams at the end (outside the timed region).
 """
 import argparse
@@ -216,7 +216,7 @@ def workload_config(args, nfr=3):
     """the `config` object both arms print (the reference arm times the same workload on the host cores)"""
     sched = ("sequential DDS (run_single/SSC0, the reference's default) in speculative batches of <= %d" % args.spec) if args.gen <= 0 else \
             ("--opt-cfg=dds,%d (run_mt/SSC1), generations of %d" % (args.gen, args.gen))
-    return {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3+rank), --best --opt-reset; step = one 20-s frame "
+    return {"workload": "configs[2]: stereo 16-bit 44.1kHz 60s synthetic WAV (seed 3, one copy per rank), --best --opt-reset; step = one 20-s frame "
                         "(882000 sample-frames): %d DDS steps, %s, window 441000, CostBitplane, k=4, search-grade kernels = %d; final pass k=1 + "
                         "bitplane payload (canonical); %d frames in flight per GPU (one host thread + stream set each)" % (args.nfunc, sched, args.grade, max(1, min(args.inflight, max(args.steps, 1)))),
             "search": "dds_sequential_speculative" if args.gen <= 0 else "dds_population", "spec": args.spec, "generation": args.gen, "grade": args.grade,
@@ -295,7 +295,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = sb.Engine(local)
-    frames = stream_frames(args.seconds, 3 + rank)
+    frames = stream_frames(args.seconds, 3)          # the same stream on every rank: equal work per GPU (weak scaling), encoded independently
     nfr = len(frames)
     inflight = max(1, min(args.inflight, max(args.steps, 1)))
     cfg = sb.make_cfg("best", num_threads=max(args.gen, 0), spec=args.spec, maxnfunc=args.nfunc, frame_parallel=2, inflight=inflight, reset=1,
