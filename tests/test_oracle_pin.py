@@ -314,3 +314,32 @@ def test_frame_search_that_moves_matches_reference():
                                    ol._p(prof, ol._f32p), cfg, ol._p(out, ol._u8p), len(out))
         assert nb > 0 and hashlib.sha1(prof.tobytes()).hexdigest() == c["profile_sha1"], c["name"]
         assert np.array_equal(np.frombuffer(out[4:4 + 58 * 4].tobytes(), np.float32), prof)
+
+
+def test_reference_best_profile_frame_record():
+    """the profile the reference CLI's own --best search ended with on the bench stream's first frame (stages of 6348 / 1873 / 335 taps,
+    OLS of 20 and 69 regressors: the parameter ranges a real search reaches, far from the default) on 110 250 sample-frames:
+    the restatement's record carries the stats, payload lengths and payload bytes of the reference's FrameCoder
+    (tests/golden/make_golden_best_profile.py, generated from libsacref_nc.so)"""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_best_profile.json")))
+    prof = np.frombuffer(bytes.fromhex(g["profile_hex"]), "<f4").copy()
+    assert sha(prof) == g["profile_sha1"]
+    pcm = synth_pcm(g["secs"], g["nch"], g["seed"]).astype(np.int32)[:g["n"]]
+    s = [np.ascontiguousarray(pcm[:, ch]) for ch in range(g["nch"])]
+    lib = ol.oracle()
+    lib.saco_set_modes(*REF)
+    cfg = (C.c_int * 8)(0, 0, 0, 0, 0, 1, ol.COST_BITPLANE, 20 * 44100)
+    out = np.zeros(8 * len(s[0]) + 4096, np.uint8)
+    p = prof.copy()
+    nb = lib.saco_encode_frame(2, len(s[0]), ol._p(s[0], ol._i32p), ol._p(s[1], ol._i32p), ol._p(p, ol._f32p), cfg, ol._p(out, ol._u8p), len(out))
+    rec = out[:nb]
+    assert np.array_equal(p, prof)
+    pos = 4 + 58 * 4
+    for ch in range(2):
+        bs = int.from_bytes(rec[pos:pos + 4].tobytes(), "little")
+        mean, mn, mx = np.frombuffer(rec[pos + 4:pos + 16].tobytes(), "<i4")
+        assert [int(mean), int(mn), int(mx), int(rec[pos + 16])] == g["stats"][ch][:4]
+        assert bs == g["payload_len"][ch] and sha(rec[pos + 18:pos + 18 + bs]) == g["payload_sha1"][ch], ch
+        pos += 18 + bs
+    assert pos == nb
