@@ -67,9 +67,11 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    """nvidia-smi clocks and throttle reasons of one GPU DURING the timed region (rank 0's GPU: the line is rank 0's). One query every
+    few seconds: a query takes the driver's lock, and the timed region lasts minutes"""
+    def __init__(self, index, period=3.0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.period = index, [], False, period
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -81,7 +83,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.5)
+            time.sleep(self.period)
 
     def summary(self):
         if not self.rows:
@@ -322,7 +324,8 @@ def main():
         eng.frames_encode(warm, [short[i % nfr] for i in range(args.warmup)], FRAME, None)
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     dd_before = eng.dedup_totals(); l_before = eng.launches; tm_before, calls_before = eng.total_timing(); gs_before = eng.grade_stats()
     t0 = time.perf_counter()
     fs, recs = run_steps(cfg, args.steps, args.warmup)
